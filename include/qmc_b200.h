@@ -1,0 +1,185 @@
+/*
+ * qmc_b200.h -- C ABI of libqmc_b200.so: the quantized-matrix-completion (QMC) maximum-likelihood
+ * hot path of shresthasagar/quantized_spectrum_cartography on NVIDIA B200 (sm_100a).
+ *
+ * Plain pointers and sizes only: no torch types, no C++ types, no exceptions across the boundary.
+ * Every function returns 0 on success and a QMC_ERR_* code otherwise; qmc_last_error() gives the
+ * message for the calling thread.  All `*_dev` pointers are device pointers on the current CUDA
+ * device, `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  The library
+ * never allocates device memory and keeps no global mutable state apart from the thread-local error
+ * string: the caller owns every buffer.  There is no CPU implementation behind these entry points.
+ *
+ * The reference is a Python module namespace, not an FFI; each entry point
+ * names the reference function(s) (file:line under /root/reference) whose arithmetic it replaces.
+ * The reference-side binding a maintainer would add is in INTEGRATION.md.
+ *
+ * Tensor layouts (the reference's, after the notebook's permutes, qmc/qmc.ipynb c1:75-81):
+ *   S  [B][R][IJ] fp32  spatial loss fields, one row per emitter   (reference: S[R,1,I,J])
+ *   C  [B][R][K]  fp32  power spectra                              (reference: C[R,K])
+ *   X  [B][K][IJ] fp32  band-major unfolding  X[k][p] = sum_r S[r][p] * C[r][k]
+ *   Y  [B][K][IJ] int64 or uint8 level indices;  Wx [B][K][IJ] fp32 0/1 mask
+ * B is the number of independent maps (1 for the reference's single-instance calls).  S may be
+ * given with arbitrary element strides (s_stride_b/r/p) so that a pixel-major [IJ][R] storage, which
+ * the batched kernel can stage with one bulk copy, is accepted as well.
+ */
+#ifndef QMC_B200_H
+#define QMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define QMC_API __attribute__((visibility("default")))
+#else
+#define QMC_API
+#endif
+
+#define QMC_ABI_VERSION 1
+#define QMC_MAX_BOUNDS 257 /* uint8 levels: at most 256 levels = 257 boundaries (qmc/utils.py:24) */
+#define QMC_MAX_RANK 32
+
+enum {
+  QMC_OK = 0,
+  QMC_ERR_INVALID = 1,     /* bad argument (shape, null pointer, unsupported size) */
+  QMC_ERR_CUDA = 2,        /* a CUDA runtime call failed; message carries cudaGetErrorString */
+  QMC_ERR_UNSUPPORTED = 3  /* valid request this build has no kernel for */
+};
+
+/* flags of qmc_likelihood_t */
+enum {
+  QMC_LOG_DOMAIN = 1u << 0,    /* x = log(t + offset) before the likelihood (qmc.ipynb c1:149) */
+  QMC_EPI_REFERENCE = 1u << 1, /* evaluate P literally as the reference does, 0.5*(1+erf(zu)) -
+                                  0.5*(1+erf(zl)) in fp32 (quantization_model.py:38,61): loses the
+                                  tails exactly where the reference does.  Default is the numerically
+                                  stable log-difference of scaled complementary error functions. */
+  QMC_FORWARD_ONLY = 1u << 2   /* NLL only, no gradients (random-restart search, qmc.ipynb c1:168-197) */
+};
+
+/*
+ * Likelihood model.  `bounds` are the boundaries as prob_probit sees them, i.e. AFTER the
+ * file-specific treatment of the two outer ones: quantization_model.py:31-33 overwrites them with
+ * -1e5/+1e5, quantization_model_log.py:32-34 leaves them alone.  The host wrapper applies that.
+ * noise_std is sigma of F_probit (quantization_model.py:57-61); the kernels use
+ * a = (float)(sigma * 1.414213) exactly like the reference (truncated sqrt 2).
+ */
+typedef struct qmc_likelihood {
+  int32_t n_bounds;  /* n boundaries => n-1 levels 0..n-2 */
+  uint32_t flags;
+  float noise_std;
+  float offset;      /* log-link offset, used when QMC_LOG_DOMAIN */
+  float bounds[QMC_MAX_BOUNDS];
+} qmc_likelihood_t;
+
+/*
+ * Compact observation set: the information content of (Y, Wx) the likelihood actually uses
+ * (only Wx != 0 entries contribute, qmc.ipynb c1:150).  Per observed entry a 4-byte linear index
+ * idx = k*IJ + p into the reference's [K][IJ] layout and a 1-byte level.  Entries are grouped into
+ * rows (map b, pixel sub-tile s, band k) -- sub-tile s covers pixels [s*sub_pixels, (s+1)*sub_pixels)
+ * -- in row-major order of (b, s, k), pixels increasing inside a row.  row_off has
+ * B*n_sub*K + 1 entries.  With n_sub == 1 this is plain band-major order.
+ */
+typedef struct qmc_obs_view {
+  const int32_t* idx_dev;
+  const uint8_t* lvl_dev;
+  const int64_t* row_off_dev;
+  int32_t n_sub;       /* pixel sub-tiles per map */
+  int32_t sub_pixels;  /* pixels per sub-tile */
+} qmc_obs_view_t;
+
+QMC_API int qmc_abi_version(void);
+QMC_API const char* qmc_last_error(void);
+/* number of kernels this library has launched on behalf of the calling process (all threads) */
+QMC_API int64_t qmc_launch_count(void);
+
+/* ---- a8: quantizer -------------------------------------------------------------------------- */
+
+/* noisy = x + noise*noise_std, or log(x + offset) + noise*noise_std when log_domain != 0, with the
+ * reference's rounding (separate multiply and add, no FMA): quantization_model.py:13,
+ * quantization_model_log.py:14.  noise_dev may be NULL (noisy = x or log(x+offset)). */
+QMC_API int qmc_noisy_signal(const float* x_dev, const float* noise_dev, float noise_std, float offset,
+                     int log_domain, int64_t n, float* noisy_out_dev, void* stream);
+
+/* Level assignment of an already-noisy signal, bit-exact with the loop of
+ * quantization_model.py:14-20: level 0 unless bounds[i] < v <= bounds[i+1] for some i in [1, n-2]
+ * (the last such i wins), the last boundary acting as +inf; NaN -> 0.  Either output may be NULL.
+ * bounds_host: the caller's ORIGINAL table (this function applies the +inf itself). */
+QMC_API int qmc_quantize_levels(const float* noisy_dev, int64_t n, const float* bounds_host, int n_bounds,
+                        uint8_t* lvl_out_dev, int64_t* y_out_dev, void* stream);
+
+/* ---- compact observation builder -------------------------------------------------------------- */
+
+/* Pass 1: count observed entries per row (b, s, k) and exclusive-scan them into row_off
+ * (B*n_sub*K + 1 int64).  wx_dev may be NULL (every entry observed).  scan_ws_dev: workspace of at
+ * least qmc_obs_scan_ws_elems(n_rows) int64.  The total is row_off[n_rows]. */
+QMC_API int64_t qmc_obs_scan_ws_elems(int64_t n_rows);
+QMC_API int qmc_obs_count_scan(const float* wx_dev, int B, int K, int IJ, int n_sub, int sub_pixels,
+                       int64_t* row_off_dev, int64_t* scan_ws_dev, void* stream);
+/* Pass 2: write idx/lvl in row order.  y is int64 (y_is_int64 != 0, the reference's dtype) or uint8. */
+QMC_API int qmc_obs_fill(const void* y_dev, int y_is_int64, const float* wx_dev, int B, int K, int IJ,
+                 int n_sub, int sub_pixels, const int64_t* row_off_dev, int32_t* idx_out_dev,
+                 uint8_t* lvl_out_dev, void* stream);
+
+/* ---- a2..a7: fused masked low-rank reconstruction + quantized NLL + factor gradients ---------- */
+
+/* algorithms of qmc_nll_fwd_bwd_gather */
+enum {
+  QMC_ALGO_AUTO = 0,
+  QMC_ALGO_FLAT = 1,  /* one thread per observed entry, factors gathered through L2, gradients by
+                         warp-aggregated global atomics: single small/medium instance */
+  QMC_ALGO_TILED = 2  /* one CTA per (map, pixel tile): factor rows staged in shared memory, band
+                         segments reduced in registers, no global atomics on gS: batched maps */
+};
+
+/*
+ * Replaces, for every map b, the reference idiom (qmc.ipynb c1:145-153)
+ *     T_hat = get_tensor(S, C).unsqueeze(1)            quantization_model.py:70-86
+ *     T_hat = torch.log(T_hat + offset)                (QMC_LOG_DOMAIN)
+ *     nll   = -torch.sum(Wx * torch.log(prob_probit(Y, T_hat, bb, std)))   :22-39, :57-61
+ *     nll.backward()  ->  S.grad, C.grad
+ * visiting only the observed entries.  nll_out_dev: B doubles; gS_out_dev: same strides as S;
+ * gC_out_dev: [B][R][K].  Gradient outputs may be NULL with QMC_FORWARD_ONLY.  Outputs are
+ * overwritten (the function zero-fills what its kernels accumulate into).
+ * tile_warps: warps per CTA of the tiled kernel = sub-tiles per pixel tile (obs.n_sub must be a
+ * multiple of it); ignored by the flat kernel.
+ */
+QMC_API int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, int64_t s_stride_r,
+                           int64_t s_stride_p, const float* C_dev, const qmc_obs_view_t* obs,
+                           const qmc_likelihood_t* lik, int B, int IJ, int K, int R, int algo,
+                           int tile_warps, double* nll_out_dev, float* gS_out_dev,
+                           float* gC_out_dev, void* stream);
+
+/* Shared-memory bytes the tiled kernel needs for a geometry (0 if it cannot run it). */
+QMC_API int64_t qmc_tiled_smem_bytes(int K, int R, int sub_pixels, int tile_warps);
+
+/*
+ * End-to-end form for callers that hold the factors in HOST memory (pinned for full speed): copies
+ * S and C to the device scratch buffers, runs qmc_nll_fwd_bwd_gather, copies nll/gS/gC back and
+ * synchronises the stream.  S_host/gS_host are dense [B][R][IJ]; scratch buffers are caller-owned
+ * device memory of the same sizes as the host arrays.
+ */
+QMC_API int qmc_nll_fwd_bwd_gather_host(const float* S_host, const float* C_host, float* S_scratch_dev,
+                                float* C_scratch_dev, const qmc_obs_view_t* obs,
+                                const qmc_likelihood_t* lik, int B, int IJ, int K, int R, int algo,
+                                int tile_warps, double* nll_scratch_dev, float* gS_scratch_dev,
+                                float* gC_scratch_dev, double* nll_host, float* gS_host,
+                                float* gC_host, void* stream);
+
+/* ---- a1/a2/a10 helpers kept importable by the reference's call surface ------------------------ */
+
+/* X[b][k][p] = sum_r S[b][r][p]*C[b][r][k] (+ optional log link): get_tensor, quantization_model.py:79-86 */
+QMC_API int qmc_get_tensor(const float* S_dev, const float* C_dev, int B, int IJ, int K, int R,
+                   float* X_out_dev, void* stream);
+
+/* sum over entries of (X_hat - X_ref)^2 and X_ref^2 for X_hat = S*C^T formed on the fly (optionally
+ * after log(. + offset)): the two Frobenius norms of NMSE / NMSE_LOG (quantization_model.py:88-92,
+ * quantization_model_log.py:104-111) without materialising X_hat.  out_dev: 2*B doubles. */
+QMC_API int qmc_nmse_terms(const float* S_dev, const float* C_dev, const float* X_ref_dev, int B, int IJ,
+                   int K, int R, int log_domain, float offset, double* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMC_B200_H */

@@ -1,0 +1,442 @@
+// Observed-entry ("gather") kernels: fused low-rank reconstruction x = <S[:,p], C[:,k]>, optional
+// log link, quantized probit NLL and the gradients w.r.t. both factors, visiting only observed
+// entries.  Replaces get_tensor -> prob_probit -> -sum(Wx*log P) -> backward of the reference
+// (qmc/quantization_model.py:22-39,57-61,70-86; caller qmc/qmc.ipynb c1:145-153).
+//
+//   flat  : one thread per observed entry, factors through L2, warp-aggregated global atomics.
+//   tiled : one CTA per (map, pixel tile); S tile, C, and both gradient tiles live in shared
+//           memory; every warp owns a pixel sub-tile exclusively, so gS updates are plain
+//           shared-memory read-modify-writes (no atomics); entries arrive sorted by band inside a
+//           sub-tile, so gC accumulates in registers and is reduced across the warp once per band.
+#include "qmc_common.cuh"
+
+namespace qmc {
+
+struct GatherParams {
+  const float* S;
+  int64_t sB, sR, sP;
+  const float* C;
+  const int32_t* idx;
+  const uint8_t* lvl;
+  const int64_t* row_off;
+  double* nll;
+  float* gS;
+  float* gC;
+  int n_sub, sub_pixels;
+  int B, IJ, K, R;
+  uint32_t div_magic;  // k = umulhi(idx, div_magic) >> div_shift  (idx < 2^31)
+  int div_shift;
+  int tiles_per_map, tile_warps;
+  float inv_a, offset;
+  float thr;  // one-bit fast path threshold
+  float bounds[QMC_MAX_BOUNDS];
+};
+
+enum : int { EPI_STABLE = 0, EPI_REFERENCE = 1, EPI_ONEBIT = 2 };
+
+__device__ __forceinline__ int fast_div(uint32_t n, uint32_t magic, int shift) {
+  return (int)(__umulhi(n, magic) >> shift);
+}
+
+template <int EPI, bool LOGD>
+__device__ __forceinline__ BinEval eval_entry(const GatherParams& prm, float t, int lvl, float& dxdt) {
+  float x = t;
+  dxdt = 1.0f;
+  if (LOGD) {
+    const float u = t + prm.offset;
+    x = logf(u);
+    dxdt = 1.0f / u;
+  }
+  if (EPI == EPI_ONEBIT) {
+    return probit_one_sided<true>(prm.thr, lvl ? 1.0f : -1.0f, x, prm.inv_a);
+  } else if (EPI == EPI_REFERENCE) {
+    return probit_bin_reference(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
+  } else {
+    return probit_bin_stable<true>(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat kernel
+// ------------------------------------------------------------------------------------------------
+template <int RP, int EPI, bool LOGD, bool GRAD>
+__global__ void __launch_bounds__(256) gather_flat_kernel(const GatherParams prm) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int64_t rows_per_map = (int64_t)prm.n_sub * prm.K;
+  const int64_t beg = prm.row_off[b * rows_per_map];
+  const int64_t end = prm.row_off[(b + 1) * rows_per_map];
+  const float* __restrict__ Sb = prm.S + b * prm.sB;
+  const float* __restrict__ Cb = prm.C + (int64_t)b * prm.R * prm.K;
+  float* gSb = GRAD ? prm.gS + b * prm.sB : nullptr;
+  float* gCb = GRAD ? prm.gC + (int64_t)b * prm.R * prm.K : nullptr;
+
+  float nll_part = 0.0f;
+  // whole warps iterate together so the shuffles below always see 32 lanes
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = beg + (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < end; base += stride) {
+    const int64_t i = base + lane;
+    const bool valid = i < end;
+    int k = 0, p = 0, lv = 0;
+    if (valid) {
+      const int id = prm.idx[i];
+      lv = prm.lvl[i];
+      k = fast_div((uint32_t)id, prm.div_magic, prm.div_shift);
+      p = id - k * prm.IJ;
+    }
+    float s[RP], c[RP];
+    float t = 0.0f;
+#pragma unroll
+    for (int r = 0; r < RP; ++r) {
+      const bool on = valid && r < prm.R;
+      s[r] = on ? __ldg(Sb + r * prm.sR + p * prm.sP) : 0.0f;
+      c[r] = on ? __ldg(Cb + r * prm.K + k) : 0.0f;
+      t = fmaf(s[r], c[r], t);
+    }
+    float g = 0.0f;
+    if (valid) {
+      float dxdt;
+      const BinEval ev = eval_entry<EPI, LOGD>(prm, t, lv, dxdt);
+      nll_part -= ev.logp;
+      g = ev.gx * dxdt;
+    }
+    if (GRAD) {
+      // gS: scattered pixels, one atomic per (entry, r)
+      if (valid) {
+#pragma unroll
+        for (int r = 0; r < RP; ++r)
+          if (r < prm.R) atomicAdd(gSb + r * prm.sR + p * prm.sP, g * c[r]);
+      }
+      // gC: entries are band-sorted, so a warp usually sees one band: aggregate, one atomic per r
+      const int k0 = __shfl_sync(0xffffffffu, k, 0);
+      const bool uniform = __all_sync(0xffffffffu, !valid || k == k0);
+      if (uniform) {
+        float v[RP];
+#pragma unroll
+        for (int r = 0; r < RP; ++r) v[r] = g * s[r];
+        const float tot = warp_transpose_sum<RP>(v, lane);
+        const int r_own = warp_transpose_owner<RP>(lane);
+        if ((lane & (32 / RP - 1)) == 0 && r_own < prm.R) atomicAdd(gCb + r_own * prm.K + k0, tot);
+      } else if (valid) {
+#pragma unroll
+        for (int r = 0; r < RP; ++r)
+          if (r < prm.R) atomicAdd(gCb + r * prm.K + k, g * s[r]);
+      }
+    }
+  }
+  // NLL: fp32 per thread (a handful of terms), fp64 from the warp level up
+  double w = warp_sum((double)nll_part);
+  __shared__ double wsum[8];
+  if (lane == 0) wsum[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += wsum[i];
+    if (tot != 0.0 || (blockIdx.x == 0)) atomicAdd(prm.nll + b, tot);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiled kernel
+// ------------------------------------------------------------------------------------------------
+// Shared memory (floats): Ssm[TP][RP] | gSsm[TP][RP] | Csm[K][RP] | gCsm[K][RP]; TP = tile pixels.
+template <int RP, int EPI, bool LOGD, bool GRAD>
+__global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams prm) {
+  extern __shared__ __align__(16) float smem[];
+  const int W = prm.tile_warps;
+  const int TP = prm.sub_pixels * W;
+  float* Ssm = smem;
+  float* gSsm = Ssm + (size_t)TP * RP;
+  float* Csm = gSsm + (GRAD ? (size_t)TP * RP : 0);
+  float* gCsm = Csm + (size_t)prm.K * RP;
+
+  const int b = blockIdx.x / prm.tiles_per_map;
+  const int tile = blockIdx.x - b * prm.tiles_per_map;
+  const int p0 = tile * TP;
+  const int np = min(TP, prm.IJ - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nthr = blockDim.x;
+
+  const float* __restrict__ Sb = prm.S + b * prm.sB;
+  const float* __restrict__ Cb = prm.C + (int64_t)b * prm.R * prm.K;
+
+  // ---- stage the factor tiles ---------------------------------------------------------------
+  if (prm.sR == 1 && RP == prm.R) {
+    // pixel-major storage: the tile is one contiguous run, copy it as it lies
+    const float* src = Sb + (int64_t)p0 * prm.sP;
+    for (int i = threadIdx.x; i < np * RP; i += nthr) Ssm[i] = __ldg(src + i);
+  } else {
+    // emitter-major storage (the reference's): coalesced row reads, transposed into [p][r]
+    for (int i = threadIdx.x; i < np * RP; i += nthr) {
+      const int r = i / np, pl = i - r * np;
+      Ssm[pl * RP + r] = (r < prm.R) ? __ldg(Sb + r * prm.sR + (int64_t)(p0 + pl) * prm.sP) : 0.0f;
+    }
+  }
+  for (int i = threadIdx.x; i < prm.K * RP; i += nthr) {
+    const int r = i / prm.K, k = i - r * prm.K;
+    Csm[k * RP + r] = (r < prm.R) ? __ldg(Cb + r * prm.K + k) : 0.0f;
+    if (GRAD) gCsm[k * RP + r] = 0.0f;
+  }
+  if (GRAD)
+    for (int i = threadIdx.x; i < np * RP; i += nthr) gSsm[i] = 0.0f;
+  __syncthreads();
+
+  // ---- this warp's entries: rows (b, tile*W + warp, 0..K-1) -------------------------------------
+  const int64_t row0 = ((int64_t)b * prm.n_sub + (int64_t)tile * W + warp) * prm.K;
+  const int64_t beg = prm.row_off[row0];
+  const int64_t end = prm.row_off[row0 + prm.K];
+
+  float nll_part = 0.0f;
+  float acc[RP];
+#pragma unroll
+  for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
+  int k_cur = -1;
+
+  auto flush = [&](int kf) {
+    if (kf < 0) return;
+    const float tot = warp_transpose_sum<RP>(acc, lane);
+    const int r_own = warp_transpose_owner<RP>(lane);
+    if ((lane & (32 / RP - 1)) == 0) atomicAdd(gCsm + kf * RP + r_own, tot);
+#pragma unroll
+    for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
+  };
+
+  for (int64_t base = beg; base < end; base += 32) {
+    const int64_t i = base + lane;
+    const bool valid = i < end;
+    int k = -1, pl = 0, lv = 0;
+    if (valid) {
+      const int id = prm.idx[i];
+      lv = prm.lvl[i];
+      k = fast_div((uint32_t)id, prm.div_magic, prm.div_shift);
+      pl = id - k * prm.IJ - p0;
+    }
+    float s[RP], c[RP];
+    float t = 0.0f;
+    const int kc = valid ? k : 0;
+#pragma unroll
+    for (int r = 0; r < RP; ++r) {
+      s[r] = Ssm[pl * RP + r];
+      c[r] = Csm[kc * RP + r];
+      t = fmaf(s[r], c[r], t);
+    }
+    float g = 0.0f;
+    if (valid) {
+      float dxdt;
+      const BinEval ev = eval_entry<EPI, LOGD>(prm, t, lv, dxdt);
+      nll_part -= ev.logp;
+      g = ev.gx * dxdt;
+    }
+    if (GRAD) {
+      // A chunk may straddle band boundaries.  Inside one band the pixels are distinct, so the
+      // lanes of that band update gS without conflicts; bands are handled one after the other.
+      unsigned todo = __ballot_sync(0xffffffffu, valid);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int kk = __shfl_sync(0xffffffffu, k, leader);
+        const bool mine = valid && k == kk;
+        if (kk != k_cur) {
+          flush(k_cur);
+          k_cur = kk;
+        }
+        if (mine) {
+#pragma unroll
+          for (int r = 0; r < RP; ++r) {
+            gSsm[pl * RP + r] = fmaf(g, c[r], gSsm[pl * RP + r]);
+            acc[r] = fmaf(g, s[r], acc[r]);
+          }
+        }
+        __syncwarp();
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+      }
+    }
+  }
+  if (GRAD) flush(k_cur);
+
+  // ---- NLL ---------------------------------------------------------------------------------------
+  double w = warp_sum((double)nll_part);
+  __shared__ double wsum[16];
+  if (lane == 0) wsum[warp] = w;
+  __syncthreads();  // also orders all gS/gC shared-memory updates before the write-back
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < W; ++i) tot += wsum[i];
+    if (prm.tiles_per_map == 1) prm.nll[b] = tot;
+    else atomicAdd(prm.nll + b, tot);
+  }
+  if (!GRAD) return;
+
+  // ---- write the gradient tiles back -------------------------------------------------------------
+  float* gSb = prm.gS + b * prm.sB;
+  if (prm.sR == 1 && RP == prm.R) {
+    float* dst = gSb + (int64_t)p0 * prm.sP;
+    for (int i = threadIdx.x; i < np * RP; i += nthr) dst[i] = gSsm[i];
+  } else {
+    for (int i = threadIdx.x; i < np * RP; i += nthr) {
+      const int r = i / np, pl = i - r * np;
+      if (r < prm.R) gSb[r * prm.sR + (int64_t)(p0 + pl) * prm.sP] = gSsm[pl * RP + r];
+    }
+  }
+  float* gCb = prm.gC + (int64_t)b * prm.R * prm.K;
+  for (int i = threadIdx.x; i < prm.K * RP; i += nthr) {
+    const int r = i / prm.K, k = i - r * prm.K;
+    if (r < prm.R) {
+      if (prm.tiles_per_map == 1) gCb[r * prm.K + k] = gCsm[k * RP + r];
+      else atomicAdd(gCb + r * prm.K + k, gCsm[k * RP + r]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+static size_t tiled_smem_bytes(int K, int RP, int sub_pixels, int W, bool grad) {
+  const size_t TP = (size_t)sub_pixels * W;
+  return ((grad ? 2 : 1) * TP * RP + 2 * (size_t)K * RP) * sizeof(float);
+}
+
+template <int RP, int EPI, bool LOGD, bool GRAD>
+static int launch_one(const GatherParams& prm, int algo, cudaStream_t st) {
+  if (algo == QMC_ALGO_FLAT) {
+    // size the grid from the average entries per map; the kernel is grid-stride
+    const int threads = 256;
+    int64_t per_map_guess = (int64_t)prm.K * prm.IJ;  // upper bound; the loop exits early
+    int64_t want = (per_map_guess + threads - 1) / threads;
+    int bx = (int)(want < 148 * 8 ? want : 148 * 8);
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, prm.B);
+    gather_flat_kernel<RP, EPI, LOGD, GRAD><<<grid, threads, 0, st>>>(prm);
+  } else {
+    const size_t smem = tiled_smem_bytes(prm.K, RP, prm.sub_pixels, prm.tile_warps, GRAD);
+    auto kern = gather_tiled_kernel<RP, EPI, LOGD, GRAD>;
+    QMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ctas = (int64_t)prm.B * prm.tiles_per_map;
+    QMC_REQUIRE(ctas <= 0x7fffffff, "too many CTAs (%lld)", (long long)ctas);
+    kern<<<(unsigned)ctas, prm.tile_warps * 32, smem, st>>>(prm);
+  }
+  count_launch();
+  QMC_CUDA_CHECK(cudaGetLastError());
+  return QMC_OK;
+}
+
+template <int RP, int EPI>
+static int launch_rp_epi(const GatherParams& prm, int algo, bool logd, bool grad, cudaStream_t st) {
+  if (logd) return grad ? launch_one<RP, EPI, true, true>(prm, algo, st) : launch_one<RP, EPI, true, false>(prm, algo, st);
+  return grad ? launch_one<RP, EPI, false, true>(prm, algo, st) : launch_one<RP, EPI, false, false>(prm, algo, st);
+}
+
+template <int RP>
+static int launch_rp(const GatherParams& prm, int algo, int epi, bool logd, bool grad, cudaStream_t st) {
+  switch (epi) {
+    case EPI_ONEBIT: return launch_rp_epi<RP, EPI_ONEBIT>(prm, algo, logd, grad, st);
+    case EPI_REFERENCE: return launch_rp_epi<RP, EPI_REFERENCE>(prm, algo, logd, grad, st);
+    default: return launch_rp_epi<RP, EPI_STABLE>(prm, algo, logd, grad, st);
+  }
+}
+
+}  // namespace qmc
+
+using namespace qmc;
+
+extern "C" int64_t qmc_tiled_smem_bytes(int K, int R, int sub_pixels, int tile_warps) {
+  if (K <= 0 || R <= 0 || R > QMC_MAX_RANK || sub_pixels <= 0 || tile_warps <= 0 || tile_warps > 16) return 0;
+  int RP = 1;
+  while (RP < R) RP <<= 1;
+  const size_t b = tiled_smem_bytes(K, RP, sub_pixels, tile_warps, true);
+  return b <= 227 * 1024 ? (int64_t)b : 0;
+}
+
+extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, int64_t s_stride_r,
+                                      int64_t s_stride_p, const float* C_dev, const qmc_obs_view_t* obs,
+                                      const qmc_likelihood_t* lik, int B, int IJ, int K, int R, int algo,
+                                      int tile_warps, double* nll_out_dev, float* gS_out_dev,
+                                      float* gC_out_dev, void* stream) {
+  QMC_REQUIRE(S_dev && C_dev && obs && lik && nll_out_dev, "null argument");
+  QMC_REQUIRE(obs->idx_dev && obs->lvl_dev && obs->row_off_dev, "null observation arrays");
+  QMC_REQUIRE(B > 0 && IJ > 0 && K > 0 && R > 0, "bad sizes B=%d IJ=%d K=%d R=%d", B, IJ, K, R);
+  QMC_REQUIRE(R <= QMC_MAX_RANK, "rank %d > %d", R, QMC_MAX_RANK);
+  QMC_REQUIRE((int64_t)K * IJ < (1LL << 31), "K*IJ = %lld does not fit the int32 linear index", (long long)K * IJ);
+  QMC_REQUIRE(lik->n_bounds >= 2 && lik->n_bounds <= QMC_MAX_BOUNDS, "n_bounds %d out of range", lik->n_bounds);
+  QMC_REQUIRE(lik->noise_std > 0.0f, "noise_std must be positive");
+  QMC_REQUIRE(obs->n_sub > 0 && obs->sub_pixels > 0 && (int64_t)obs->n_sub * obs->sub_pixels >= IJ,
+              "sub-tiles (%d x %d) do not cover IJ=%d", obs->n_sub, obs->sub_pixels, IJ);
+  const bool grad = !(lik->flags & QMC_FORWARD_ONLY);
+  QMC_REQUIRE(!grad || (gS_out_dev && gC_out_dev), "gradient outputs are NULL without QMC_FORWARD_ONLY");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  GatherParams prm;
+  prm.S = S_dev; prm.sB = s_stride_b; prm.sR = s_stride_r; prm.sP = s_stride_p;
+  prm.C = C_dev; prm.idx = obs->idx_dev; prm.lvl = obs->lvl_dev; prm.row_off = obs->row_off_dev;
+  prm.nll = nll_out_dev; prm.gS = gS_out_dev; prm.gC = gC_out_dev;
+  prm.n_sub = obs->n_sub; prm.sub_pixels = obs->sub_pixels;
+  prm.B = B; prm.IJ = IJ; prm.K = K; prm.R = R;
+  // exact division of any idx < 2^31 by IJ (Granlund-Montgomery with N = 31: l = ceil(log2 IJ),
+  // m = floor(2^(31+l)/IJ) + 1 fits 32 bits, q = (m*n) >> (31+l) = umulhi(n, m) >> (l-1))
+  QMC_REQUIRE(IJ > 1, "IJ must be > 1");
+  int l = 0;
+  while ((1LL << l) < IJ) ++l;
+  prm.div_magic = (uint32_t)(((1ULL << (31 + l)) / (uint64_t)IJ) + 1ULL);
+  prm.div_shift = l - 1;
+  const float a = probit_scale(lik->noise_std);
+  prm.inv_a = 1.0f / a;
+  prm.offset = lik->offset;
+  for (int i = 0; i < lik->n_bounds; ++i) prm.bounds[i] = lik->bounds[i];
+  prm.thr = lik->n_bounds >= 3 ? lik->bounds[1] : 0.0f;
+
+  // epilogue: reference-literal, one-bit fast path (both outer bounds numerically infinite), or general
+  int epi = EPI_STABLE;
+  if (lik->flags & QMC_EPI_REFERENCE) epi = EPI_REFERENCE;
+  else if (lik->n_bounds == 3) {
+    // erfc(z) == 0 exactly (even in double) for z > 27; require the sentinel to sit that far out for
+    // any |x| < half its magnitude
+    const float lo = lik->bounds[0], hi = lik->bounds[2];
+    const bool inf_lo = lo < 0 && (-lo * 0.5f) * prm.inv_a > 30.0f;
+    const bool inf_hi = hi > 0 && (hi * 0.5f) * prm.inv_a > 30.0f;
+    if (inf_lo && inf_hi && fabsf(lo) >= 1e4f && fabsf(hi) >= 1e4f) epi = EPI_ONEBIT;
+  }
+  const bool logd = (lik->flags & QMC_LOG_DOMAIN) != 0;
+
+  int RP = 1;
+  while (RP < R) RP <<= 1;
+
+  if (algo == QMC_ALGO_AUTO) {
+    const int64_t smem = qmc_tiled_smem_bytes(K, R, obs->sub_pixels, tile_warps > 0 ? tile_warps : 1);
+    algo = (tile_warps > 0 && smem > 0 && obs->n_sub % tile_warps == 0 && (int64_t)B * (obs->n_sub / tile_warps) >= 64)
+               ? QMC_ALGO_TILED : QMC_ALGO_FLAT;
+  }
+  if (algo == QMC_ALGO_TILED) {
+    QMC_REQUIRE(tile_warps > 0 && tile_warps <= 16, "tile_warps %d out of range", tile_warps);
+    QMC_REQUIRE(obs->n_sub % tile_warps == 0, "n_sub %d is not a multiple of tile_warps %d", obs->n_sub, tile_warps);
+    QMC_REQUIRE(tiled_smem_bytes(K, RP, obs->sub_pixels, tile_warps, grad) <= 227 * 1024,
+                "tile of %d pixels x rank %d does not fit shared memory", obs->sub_pixels * tile_warps, RP);
+    prm.tile_warps = tile_warps;
+    prm.tiles_per_map = obs->n_sub / tile_warps;
+  } else if (algo == QMC_ALGO_FLAT) {
+    prm.tile_warps = 0; prm.tiles_per_map = 0;
+  } else {
+    return set_error(QMC_ERR_INVALID, "unknown algo %d", algo);
+  }
+
+  // zero what the kernels accumulate into
+  const bool atomics_on_out = (algo == QMC_ALGO_FLAT) || prm.tiles_per_map > 1;
+  if (atomics_on_out) {
+    QMC_CUDA_CHECK(cudaMemsetAsync(nll_out_dev, 0, sizeof(double) * B, st));
+    if (grad) QMC_CUDA_CHECK(cudaMemsetAsync(gC_out_dev, 0, sizeof(float) * (size_t)B * R * K, st));
+  }
+  if (grad && algo == QMC_ALGO_FLAT) {
+    // gS may be strided: zero the dense extent it spans only when it is compact
+    const bool dense = (s_stride_p == 1 && s_stride_r == IJ) || (s_stride_r == 1 && s_stride_p == R);
+    QMC_REQUIRE(dense && s_stride_b == (int64_t)R * IJ, "flat kernel needs a compact gS layout");
+    QMC_CUDA_CHECK(cudaMemsetAsync(gS_out_dev, 0, sizeof(float) * (size_t)B * R * IJ, st));
+  }
+
+  switch (RP) {
+    case 1: return launch_rp<1>(prm, algo, epi, logd, grad, st);
+    case 2: return launch_rp<2>(prm, algo, epi, logd, grad, st);
+    case 4: return launch_rp<4>(prm, algo, epi, logd, grad, st);
+    case 8: return launch_rp<8>(prm, algo, epi, logd, grad, st);
+    case 16: return launch_rp<16>(prm, algo, epi, logd, grad, st);
+    case 32: return launch_rp<32>(prm, algo, epi, logd, grad, st);
+  }
+  return set_error(QMC_ERR_UNSUPPORTED, "rank %d", R);
+}

@@ -1,0 +1,67 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/qmc_b200.h declares.
+No compute calls here (there is no GPU in the build container)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "qmc_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"^QMC_API\s+[\w\s\*]+?\b(qmc_\w+)\s*\(", text, flags=re.M)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for must in ("qmc_quantize_levels", "qmc_obs_count_scan", "qmc_obs_fill", "qmc_nll_fwd_bwd_gather",
+                 "qmc_nll_fwd_bwd_gather_host", "qmc_abi_version", "qmc_last_error"):
+        assert must in syms, must
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from quantized_spectrum_cartography_b200 import build as qbuild
+    path = qbuild.build()
+    lib = ctypes.CDLL(path)
+    for sym in declared_symbols():
+        assert hasattr(lib, sym), f"{sym} declared in include/qmc_b200.h but not exported by {path}"
+    lib.qmc_abi_version.restype = ctypes.c_int
+    assert lib.qmc_abi_version() == int(re.search(r"#define QMC_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
+
+
+def test_python_binding_covers_every_declared_symbol():
+    from quantized_spectrum_cartography_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+
+
+def test_argument_validation_needs_no_gpu():
+    """Invalid arguments are rejected before any CUDA call, with a message."""
+    from quantized_spectrum_cartography_b200 import _lib
+    rc = _lib.lib.qmc_quantize_levels(None, 10, None, 3, None, None, None)
+    assert rc == 1 and b"bad arguments" in _lib.lib.qmc_last_error()
+    with pytest.raises(_lib.QmcError):
+        _lib.check(rc)
+    assert _lib.lib.qmc_tiled_smem_bytes(64, 4, 326, 8) == (2 * 326 * 8 * 4 + 2 * 64 * 4) * 4
+    assert _lib.lib.qmc_tiled_smem_bytes(64, 4, 100000, 8) == 0
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "quantized_spectrum_cartography_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_plan_tiles_covers_the_map():
+    from quantized_spectrum_cartography_b200.obs import plan_tiles
+    for IJ, K, R in ((2601, 64, 4), (10201, 128, 8), (262144, 256, 16), (7, 3, 1), (2601, 64, 3)):
+        n_sub, sub, tw = plan_tiles(IJ, K, R)
+        assert n_sub % tw == 0 and n_sub * sub >= IJ
+        assert (n_sub - tw) * sub < IJ or n_sub == tw      # no entirely empty trailing tile
+    assert plan_tiles(2601, 64, 4) == (8, 326, 8)          # cfg1/cfg3: one CTA per map
