@@ -75,8 +75,10 @@ def test_device_side_noisy_signal_is_bit_exact(q):
     for std, off in ((1e-3, None), (0.5, 2.27e-5)):
         want = oc.noisy_signal(x, n, std, off)
         out = torch.empty_like(x, device="cuda")
-        check(lib.qmc_noisy_signal(x.cuda().data_ptr(), n.cuda().data_ptr(), std, 0.0 if off is None else off,
+        xd, nd = x.cuda(), n.cuda()          # keep the device copies alive across the call
+        check(lib.qmc_noisy_signal(xd.data_ptr(), nd.data_ptr(), std, 0.0 if off is None else off,
                                    int(off is not None), x.numel(), out.data_ptr(), None))
+        torch.cuda.synchronize()
         if off is None:
             assert torch.equal(out.cpu(), want)          # IEEE multiply and add: bit-identical
         else:
@@ -141,17 +143,24 @@ def test_fused_nll_and_gradients_vs_reference(tag, q, nll_golden, fixture_instan
             assert rel_err(C.grad.numpy(), c["gC"].numpy()) < GRAD_RTOL
 
 
-def test_reference_epilogue_reproduces_the_reference_tail_loss(q, nll_golden, fixture_instance):
-    """QMC_EPI_REFERENCE evaluates P literally like the reference; at sigma = 1e-4 / zero start the
-    reference is 2.6e-3 away from the float64 truth (min P = 3e-7) and so is this mode, while the
-    default stable epilogue is not."""
+def test_reference_epilogue_loses_the_tails_like_the_reference(q, nll_golden, fixture_instance):
+    """QMC_EPI_REFERENCE evaluates P literally like the reference, 0.5*(1+erf(zu)) - 0.5*(1+erf(zl))
+    in fp32.  At sigma = 1e-4 / zero start min P is 5 * 2^-24: P is quantised to multiples of 2^-24,
+    so the result depends on the last bit of the erf implementation -- the reference (torch CPU erf)
+    is 2.6e-3 away from the float64 truth and the literal CUDA mode (erff) is off by a similar
+    amount in its own direction.  Neither is 'right'; the default stable epilogue is."""
     c = nll_case_inputs(nll_golden, fixture_instance, "lin2_s1e-4__zero")
     nll64 = oc.nll_and_grads_fp64(c["S"], c["C"], c["Y"], c["Wx"], c["bb"], c["sigma"])[0]
     lit = q.qmc_nll(c["S"], c["C"], c["Y"], c["Wx"], c["bb"], c["sigma"], reference_epilogue=True).item()
     stable = q.qmc_nll(c["S"], c["C"], c["Y"], c["Wx"], c["bb"], c["sigma"]).item()
     assert abs(c["nll"] / nll64 - 1) > 1e-3                 # the reference's own loss of accuracy
-    assert lit == pytest.approx(c["nll"], rel=2e-4)          # reproduced (erff vs torch.erf last-place noise)
+    assert abs(lit / nll64 - 1) > 1e-3                      # same disease, literal CUDA statement
+    assert abs(lit / c["nll"] - 1) < 5e-2                   # ... and the same order of magnitude
     assert stable == pytest.approx(nll64, rel=NLL_RTOL)
+    # where the reference is accurate the literal mode agrees with it to fp32 noise
+    c = nll_case_inputs(nll_golden, fixture_instance, "lin2_s8e-3__p08")
+    lit = q.qmc_nll(c["S"], c["C"], c["Y"], c["Wx"], c["bb"], c["sigma"], reference_epilogue=True).item()
+    assert lit == pytest.approx(c["nll"], rel=NLL_RTOL)
 
 
 def _random_instance(B, I, J, K, R, f, levels, seed, log_domain=False):
@@ -223,8 +232,9 @@ def test_tiled_kernel_pixel_major_storage_and_full_size_map(q):
     nll_e, gS_e, gC_e = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs_t, lik, algo=_lib.QMC_ALGO_TILED)
     nll_f, gS_f, gC_f = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs_f, lik, algo=_lib.QMC_ALGO_FLAT)
     assert gS_t.stride() == S_pm.stride()
-    np.testing.assert_allclose(nll_t.cpu().numpy(), nll_f.cpu().numpy(), rtol=1e-9)
-    np.testing.assert_allclose(nll_e.cpu().numpy(), nll_f.cpu().numpy(), rtol=1e-9)
+    # (fp32 per-thread partial sums are grouped differently by the two kernels)
+    np.testing.assert_allclose(nll_t.cpu().numpy(), nll_f.cpu().numpy(), rtol=2e-7)
+    np.testing.assert_allclose(nll_e.cpu().numpy(), nll_f.cpu().numpy(), rtol=2e-7)
     assert rel_err(gS_t.cpu().numpy(), gS_f.cpu().numpy()) < 1e-5
     assert rel_err(gS_e.cpu().numpy(), gS_f.cpu().numpy()) < 1e-5
     assert rel_err(gC_t.cpu().numpy(), gC_f.cpu().numpy()) < 1e-5
@@ -281,7 +291,8 @@ def test_thin_compositional_surface(q, fixture_instance):
     np.testing.assert_allclose(qm.F_probit(torch.from_numpy(m["F_probit_x"]), 0.008).numpy(), m["F_probit_y"], rtol=2e-6, atol=2e-7)
     bb7 = torch.from_numpy(t["QUANTIZATION_BOUNDARIES_7_ADJUSTED"])
     np.testing.assert_array_equal(ql.get_quantized_obs_from_ordinal(torch.arange(7), bb7, 0.5).numpy(), m["midpoints"])
-    assert qm.DeterministicCost(mean=5e-4)(0.8 * S, C, 2 * target - 1).item() == pytest.approx(float(m["determ_cost"]), rel=1e-5)
+    # (a difference of two fp32 sums over 166k entries: CPU and GPU summation orders differ)
+    assert qm.DeterministicCost(mean=5e-4)(0.8 * S, C, 2 * target - 1).item() == pytest.approx(float(m["determ_cost"]), rel=1e-4)
     # the hand-composed idiom still works and agrees with the fused op where the reference is accurate
     Sg = (0.8 * S).clone().requires_grad_(True)
     Cg = C.clone().requires_grad_(True)
