@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Headline benchmark of the QMC quantized-likelihood hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+Workload (config.workload = "cfg3"): batched recovery of 4096 independent 51x51x64 one-bit maps,
+rank R = 4, 10 % per-entry sampling -- BASELINE.json configs[2], the configuration the metric's
+"% HBM roofline" is meaningful on (a single cfg1/cfg2 instance moves 0.2-2 MB and is pure launch
+latency).  One *step* = one evaluation of the whole batch: fused NLL forward
++ gradients w.r.t. S and C.  With N GPUs every rank owns its own 4096 maps (weak scaling, no
+collective on the data path); `value` = observed entries of all ranks / max-over-ranks time.
+
+Printed JSON (one line, rank 0): the base contract's keys plus
+  roofline     -- algorithmic bytes per launch / mean launch time, against the measured HBM peak
+  cpu_baseline -- the oracle's torch-CPU port of the reference algorithm, timed on this box's cores
+  e2e          -- same metric through the host-buffer C-ABI call (H2D of S,C and D2H of nll,gS,gC
+                  inside the timed region)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG3 = dict(workload="cfg3", maps=4096, I=51, J=51, K=64, R=4, sampling=0.10, levels=2)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--maps", type=int, default=CFG3["maps"], help="maps per GPU (default: the cfg3 batch)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--layout", default="pixel_major", choices=["pixel_major", "emitter_major"],
+                    help="device storage of S for the kernel-only number")
+    return ap.parse_args()
+
+
+# -------------------------------------------------------------------------------------------------
+# clocks
+# -------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------------------
+# workload
+# -------------------------------------------------------------------------------------------------
+def build_workload(n_maps: int, device, seed: int):
+    """cfg3 on one GPU: synthetic maps, one-bit observations, tiled compact observation set.
+    Seeds: `seed` data, `seed+1` noise and mask."""
+    import torch
+
+    import quantized_spectrum_cartography_b200 as q
+    from quantized_spectrum_cartography_b200 import _lib, synth
+    from quantized_spectrum_cartography_b200._lib import check, lib
+
+    c = CFG3
+    I, J, K, R = c["I"], c["J"], c["K"], c["R"]
+    IJ = I * J
+    maps = synth.generate_maps(n_maps, I, J, K, R, seed=seed, device=device)
+    T = maps.tensor()                                                    # [B, K, IJ]
+    thr = T.reshape(-1)[:: max(1, T.numel() // 2_000_000)].median().item()
+    sigma = thr                                                          # keeps the fp32 reference finite
+    bb = torch.tensor([0.0, thr, 1.0])
+    gen = torch.Generator(device=device).manual_seed(seed + 1)
+    noise = torch.randn(T.shape, device=device, generator=gen)
+    noisy = torch.empty_like(T)
+    check(lib.qmc_noisy_signal(T.data_ptr(), noise.data_ptr(), sigma, 0.0, 0, T.numel(), noisy.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream))
+    del noise
+    Y = torch.empty(T.shape, dtype=torch.uint8, device=device)
+    import ctypes as C
+    arr = (C.c_float * 3)(*bb.tolist())
+    check(lib.qmc_quantize_levels(noisy.data_ptr(), noisy.numel(), arr, 3, Y.data_ptr(), None,
+                                  torch.cuda.current_stream().cuda_stream))
+    del noisy
+    Wx = torch.bernoulli(torch.full(T.shape, c["sampling"], device=device), generator=gen)
+    n_sub, sub, tw = q.plan_tiles(IJ, K, R)
+    obs = q.build_obs(Y, Wx, K, IJ, n_maps, n_sub=n_sub, sub_pixels=sub, tile_warps=tw)
+    lik = q.make_likelihood(bb, sigma)
+    S_eval = (0.8 * maps.S_true).contiguous()                            # evaluation point
+    C_eval = maps.C_true.contiguous()
+    host_sample = dict(Y=Y[:256].cpu(), Wx=Wx[:256].cpu(), S=S_eval[:256].cpu(), C=C_eval[:256].cpu(),
+                       bb=bb, sigma=sigma)
+    del T, Y, Wx
+    torch.cuda.empty_cache()
+    return dict(obs=obs, lik=lik, S=S_eval, C=C_eval, IJ=IJ, K=K, R=R, I=I, J=J, host_sample=host_sample,
+                thr=thr, sigma=sigma)
+
+
+def cpu_reference_sample(hs, I, J, K, R, budget_s: float, vectorised: bool = False, max_maps: int = 256):
+    """Time the oracle's torch-CPU port of the reference algorithm (get_tensor -> prob_probit ->
+    -sum(Wx*log P) -> backward) map by map until the budget is spent.  Returns (obs/s, maps, seconds)."""
+    import torch
+
+    from oracle import qmc_oracle as oc
+    torch.set_num_threads(os.cpu_count() or 1)
+    n_obs, t_used, done = 0, 0.0, 0
+    for b in range(min(max_maps, hs["S"].shape[0])):
+        S = hs["S"][b].reshape(R, 1, I, J)
+        Cm = hs["C"][b]
+        Y = hs["Y"][b].reshape(K, 1, I, J).long()
+        Wx = hs["Wx"][b].reshape(K, 1, I, J)
+        t0 = time.perf_counter()
+        nll, gS, gC = oc.nll_and_grads(S, Cm, Y, Wx, hs["bb"], hs["sigma"], vectorised=vectorised)
+        t_used += time.perf_counter() - t0
+        assert torch.isfinite(nll), "reference NLL is not finite on the benchmark workload"
+        n_obs += int(Wx.sum().item())
+        done += 1
+        if t_used >= budget_s:
+            break
+    return n_obs / t_used, done, t_used
+
+
+# -------------------------------------------------------------------------------------------------
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's own CPU algorithm (oracle port; the reference is Python and
+    /root/reference does not exist on the GPU box) on this box's host cores.  Rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    c = CFG3
+    # a 256-map slice of the same workload is all the CPU arm ever touches
+    if dev.type == "cuda":
+        wl = build_workload(256, dev, seed=0)
+        hs = wl["host_sample"]
+    else:
+        raise SystemExit(json.dumps({"impl": "reference", "unavailable": "no CUDA device to synthesise the workload"}))
+    maps_per_step = 8
+    per_step = []
+    n_obs_step = []
+    torch.set_num_threads(os.cpu_count() or 1)
+    from oracle import qmc_oracle as oc
+    I, J, K, R = c["I"], c["J"], c["K"], c["R"]
+
+    def step(i):
+        tot = 0
+        for b in range(maps_per_step):
+            m = (i * maps_per_step + b) % hs["S"].shape[0]
+            Wx = hs["Wx"][m].reshape(K, 1, I, J)
+            oc.nll_and_grads(hs["S"][m].reshape(R, 1, I, J), hs["C"][m], hs["Y"][m].reshape(K, 1, I, J).long(), Wx,
+                             hs["bb"], hs["sigma"])
+            tot += int(Wx.sum().item())
+        return tot
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    total = 0
+    for i in range(args.steps):
+        total += step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    value = total / dt
+    cores = torch.get_num_threads()
+    sample = f"{maps_per_step} of {c['maps']} maps per step, {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": "QMC observed-entries/s (fused NLL fwd + gS + gC)", "value": value,
+        "unit": "observed-entries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": c["workload"], "maps_per_gpu": c["maps"], "shape": "51x51x64", "rank": c["R"],
+                   "sampling": c["sampling"], "levels": c["levels"]},
+        "cpu_baseline": {"value": value, "unit": "observed-entries/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "observed-entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_b200(args, rank: int, world: int, local_rank: int):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import quantized_spectrum_cartography_b200 as q
+    from quantized_spectrum_cartography_b200 import _lib
+    from quantized_spectrum_cartography_b200._lib import check, lib
+
+    wl = build_workload(args.maps, dev, seed=2 * rank)
+    obs, lik, R, K, IJ = wl["obs"], wl["lik"], wl["R"], wl["K"], wl["IJ"]
+    B = args.maps
+    S = wl["S"]
+    if args.layout == "pixel_major":
+        S = S.transpose(1, 2).contiguous().transpose(1, 2)     # [B,R,IJ] view of [B,IJ,R] storage
+    Cf = wl["C"]
+    nll = torch.empty(B, dtype=torch.float64, device=dev)
+    gS = torch.empty_strided(S.shape, S.stride(), dtype=torch.float32, device=dev)
+    gC = torch.empty_like(Cf)
+    view = obs.view()
+    stream = torch.cuda.current_stream()
+
+    def step():
+        check(lib.qmc_nll_fwd_bwd_gather(S.data_ptr(), S.stride(0), S.stride(1), S.stride(2), Cf.data_ptr(),
+                                         C.byref(view), C.byref(lik), B, IJ, K, R, _lib.QMC_ALGO_TILED,
+                                         obs.tile_warps, nll.data_ptr(), gS.data_ptr(), gC.data_ptr(),
+                                         stream.cuda_stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0 = _lib.launch_count()
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(stream)
+    barrier()
+    launches = _lib.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks, units summed over ranks
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    n = torch.tensor([float(obs.nobs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    total_ms = t.item()
+    nobs_all = n.item()
+    value = nobs_all * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        Sh = wl["S"].cpu().pin_memory()
+        Ch = wl["C"].cpu().pin_memory()
+        gSh = torch.empty_like(Sh).pin_memory()
+        gCh = torch.empty_like(Ch).pin_memory()
+        nllh = torch.empty(B, dtype=torch.float64).pin_memory()
+        Sd, gSd = torch.empty_like(wl["S"]), torch.empty_like(wl["S"])
+        Cd, gCd = torch.empty_like(Cf), torch.empty_like(Cf)
+
+        def e2e_step():
+            check(lib.qmc_nll_fwd_bwd_gather_host(
+                Sh.data_ptr(), Ch.data_ptr(), Sd.data_ptr(), Cd.data_ptr(), C.byref(view), C.byref(lik), B, IJ, K, R,
+                _lib.QMC_ALGO_TILED, obs.tile_warps, nll.data_ptr(), gSd.data_ptr(), gCd.data_ptr(), nllh.data_ptr(),
+                gSh.data_ptr(), gCh.data_ptr(), stream.cuda_stream))
+
+        for _ in range(max(3, min(args.warmup, 5))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()                     # synchronises the stream itself: results are on the host
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = Sh.numel() * 4 + Ch.numel() * 4
+        d2h = gSh.numel() * 4 + gCh.numel() * 4 + nllh.numel() * 8
+        e2e = {"value": nobs_all * args.steps / te.item(), "unit": "observed-entries/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "qmc_nll_fwd_bwd_gather_host (C ABI, pinned host S/C in, nll/gS/gC out; observation set resident)"}
+        assert torch.isfinite(nllh).all()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline -----------------------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = obs.algorithmic_bytes(R)
+    mean_launch_ms = statistics.mean(per_launch_ms)
+    achieved = alg_bytes / (mean_launch_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "gather_tiled_kernel<4,ONEBIT>",
+                "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_launch_ms,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, nmaps, secs = cpu_reference_sample(wl["host_sample"], wl["I"], wl["J"], K, R, args.cpu_seconds)
+        vf, nmaps_f, secs_f = cpu_reference_sample(wl["host_sample"], wl["I"], wl["J"], K, R,
+                                                   min(4.0, args.cpu_seconds), vectorised=True)
+        import torch as _t
+        cpu = {"value": v, "unit": "observed-entries/s", "cores": _t.get_num_threads(), "kind": "port",
+               "sample": f"first {nmaps} of {B} maps, fwd+bwd, {secs:.1f} s of CPU work",
+               "value_vectorised_fair_cpu": vf}
+
+    c = CFG3
+    out = {
+        "metric": "QMC observed-entries/s (fused NLL fwd + gS + gC)", "value": value, "unit": "observed-entries/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": c["workload"], "maps_per_gpu": B, "shape": "51x51x64", "rank": R,
+                   "sampling": c["sampling"], "levels": c["levels"], "observed_entries_per_gpu": obs.nobs,
+                   "S_layout": args.layout, "l2": "inputs %.2f GB/step per GPU > 126 MB L2 (no flush needed)" % (alg_bytes / 1e9),
+                   "evaluation_point": "0.8*S_true, C_true", "threshold": wl["thr"], "sigma": wl["sigma"]},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "evaluations_per_s": args.steps / (total_ms * 1e-3) * world,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # not launched by torchrun: do it ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
