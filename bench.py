@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tile-warps", type=int, default=8)
+    ap.add_argument("--smem-budget-kb", type=int, default=100)
     ap.add_argument("--layout", default="pixel_major", choices=["pixel_major", "emitter_major"],
                     help="device storage of S for the kernel-only number")
     return ap.parse_args()
@@ -105,7 +107,7 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # workload
 # -------------------------------------------------------------------------------------------------
-def build_workload(n_maps: int, device, seed: int):
+def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_budget_kb: int = 100):
     """cfg3 on one GPU: synthetic maps, one-bit observations, tiled compact observation set.
     Seeds: `seed` data, `seed+1` noise and mask."""
     import torch
@@ -135,7 +137,7 @@ def build_workload(n_maps: int, device, seed: int):
                                   torch.cuda.current_stream().cuda_stream))
     del noisy
     Wx = torch.bernoulli(torch.full(T.shape, c["sampling"], device=device), generator=gen)
-    n_sub, sub, tw = q.plan_tiles(IJ, K, R)
+    n_sub, sub, tw = q.plan_tiles(IJ, K, R, tile_warps, smem_budget_kb * 1024)
     obs = q.build_obs(Y, Wx, K, IJ, n_maps, n_sub=n_sub, sub_pixels=sub, tile_warps=tw)
     lik = q.make_likelihood(bb, sigma)
     S_eval = (0.8 * maps.S_true).contiguous()                            # evaluation point
@@ -242,7 +244,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     from quantized_spectrum_cartography_b200 import _lib
     from quantized_spectrum_cartography_b200._lib import check, lib
 
-    wl = build_workload(args.maps, dev, seed=2 * rank)
+    wl = build_workload(args.maps, dev, seed=2 * rank, tile_warps=args.tile_warps, smem_budget_kb=args.smem_budget_kb)
     obs, lik, R, K, IJ = wl["obs"], wl["lik"], wl["R"], wl["K"], wl["IJ"]
     B = args.maps
     S = wl["S"]
@@ -370,7 +372,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": c["workload"], "maps_per_gpu": B, "shape": "51x51x64", "rank": R,
                    "sampling": c["sampling"], "levels": c["levels"], "observed_entries_per_gpu": obs.nobs,
-                   "S_layout": args.layout, "l2": "inputs %.2f GB/step per GPU > 126 MB L2 (no flush needed)" % (alg_bytes / 1e9),
+                   "S_layout": args.layout, "tile_warps": obs.tile_warps, "tiles_per_map": obs.n_sub // obs.tile_warps, "l2": "inputs %.2f GB/step per GPU > 126 MB L2 (no flush needed)" % (alg_bytes / 1e9),
                    "evaluation_point": "0.8*S_true, C_true", "threshold": wl["thr"], "sigma": wl["sigma"]},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "evaluations_per_s": args.steps / (total_ms * 1e-3) * world,

@@ -139,16 +139,76 @@ __global__ void __launch_bounds__(256) gather_flat_kernel(const GatherParams prm
 // ------------------------------------------------------------------------------------------------
 // tiled kernel
 // ------------------------------------------------------------------------------------------------
-// Shared memory (floats): Ssm[TP][RP] | gSsm[TP][RP] | Csm[K][RP] | gCsm[K][RP]; TP = tile pixels.
-template <int RP, int EPI, bool LOGD, bool GRAD>
+// One CTA per (map, pixel tile), tile_warps warps; warp w owns pixel sub-tile (tile*W + w) exclusively
+// and walks its entries -- one contiguous stream, rows (bands) in increasing order -- 32*UNR at a
+// time.  Shared memory (floats):
+//   Ssm[TP][RP] | gSsm[TP][RP] | Csm[K][RP] | gCw[Wc][K][RP] | offs[W][K+2] (int)
+// TP = tile pixels.  gCw holds one private copy of gC per warp (Wc = W) when that fits, otherwise a
+// single copy updated with shared-memory atomics (Wc = 1).
+//
+// Per 32-entry chunk: phase A (pure math, UNR chunks interleaved for ILP) computes x, log P and
+// g = dNLL/dt for every entry; phase B applies the gradient updates band segment by band segment:
+// inside one band the pixels of a sub-tile are distinct, so gS is a plain shared-memory
+// read-modify-write; gC accumulates in registers and is reduced across the warp once per band.
+
+constexpr size_t kPrivateGcBytes = 32 * 1024;
+
+__host__ __device__ inline bool gc_private(int K, int RP, int W) {
+  return (size_t)W * K * RP * sizeof(float) <= kPrivateGcBytes;
+}
+
+static size_t tiled_smem_bytes(int K, int RP, int sub_pixels, int W, bool grad) {
+  const size_t TP = (size_t)sub_pixels * W;
+  const size_t wc = gc_private(K, RP, W) ? W : 1;
+  size_t fl = TP * RP + (size_t)K * RP;
+  if (grad) fl += TP * RP + wc * K * RP;
+  return fl * sizeof(float) + (size_t)W * (K + 2) * sizeof(int) + 16;
+}
+
+// ---- bulk (TMA) copies of a contiguous tile ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int RP, int EPI, bool LOGD, bool GRAD, int UNR>
 __global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams prm) {
   extern __shared__ __align__(16) float smem[];
-  const int W = prm.tile_warps;
+  const int W = prm.tile_warps, K = prm.K;
   const int TP = prm.sub_pixels * W;
+  const bool priv = gc_private(K, RP, W);
   float* Ssm = smem;
-  float* gSsm = Ssm + (size_t)TP * RP;
-  float* Csm = gSsm + (GRAD ? (size_t)TP * RP : 0);
-  float* gCsm = Csm + (size_t)prm.K * RP;
+  float* Csm = Ssm + (size_t)TP * RP;
+  float* gSsm = Csm + (size_t)K * RP;
+  float* gCw = gSsm + (GRAD ? (size_t)TP * RP : 0);
+  int* offs = reinterpret_cast<int*>(gCw + (GRAD ? (size_t)(priv ? W : 1) * K * RP : 0));
+  __shared__ uint64_t mbar;
+  __shared__ double wsum[16];
 
   const int b = blockIdx.x / prm.tiles_per_map;
   const int tile = blockIdx.x - b * prm.tiles_per_map;
@@ -158,104 +218,158 @@ __global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams pr
   const int nthr = blockDim.x;
 
   const float* __restrict__ Sb = prm.S + b * prm.sB;
-  const float* __restrict__ Cb = prm.C + (int64_t)b * prm.R * prm.K;
+  const float* __restrict__ Cb = prm.C + (int64_t)b * prm.R * K;
+  // pixel-major storage ([IJ][R], R == RP a multiple of 4): the tile is one contiguous, 16-byte
+  // aligned run -> one TMA bulk copy in, one out
+  const bool bulk = (prm.sR == 1 && prm.sP == RP && prm.R == RP && (RP % 4) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(Sb) | (GRAD ? reinterpret_cast<uintptr_t>(prm.gS + b * prm.sB) : 0)) & 15) == 0);
 
   // ---- stage the factor tiles ---------------------------------------------------------------
-  if (prm.sR == 1 && RP == prm.R) {
-    // pixel-major storage: the tile is one contiguous run, copy it as it lies
-    const float* src = Sb + (int64_t)p0 * prm.sP;
-    for (int i = threadIdx.x; i < np * RP; i += nthr) Ssm[i] = __ldg(src + i);
+  if (bulk) {
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)np * RP * sizeof(float);
+      mbar_expect_tx(&mbar, bytes);
+      bulk_g2s(Ssm, Sb + (int64_t)p0 * RP, bytes, &mbar);
+    }
   } else {
     // emitter-major storage (the reference's): coalesced row reads, transposed into [p][r]
-    for (int i = threadIdx.x; i < np * RP; i += nthr) {
-      const int r = i / np, pl = i - r * np;
-      Ssm[pl * RP + r] = (r < prm.R) ? __ldg(Sb + r * prm.sR + (int64_t)(p0 + pl) * prm.sP) : 0.0f;
-    }
+#pragma unroll
+    for (int r = 0; r < RP; ++r)
+      for (int pl = threadIdx.x; pl < np; pl += nthr)
+        Ssm[pl * RP + r] = (r < prm.R) ? __ldg(Sb + r * prm.sR + (int64_t)(p0 + pl) * prm.sP) : 0.0f;
   }
-  for (int i = threadIdx.x; i < prm.K * RP; i += nthr) {
-    const int r = i / prm.K, k = i - r * prm.K;
-    Csm[k * RP + r] = (r < prm.R) ? __ldg(Cb + r * prm.K + k) : 0.0f;
-    if (GRAD) gCsm[k * RP + r] = 0.0f;
-  }
-  if (GRAD)
+#pragma unroll
+  for (int r = 0; r < RP; ++r)
+    for (int k = threadIdx.x; k < K; k += nthr) Csm[k * RP + r] = (r < prm.R) ? __ldg(Cb + r * K + k) : 0.0f;
+  if (GRAD) {
     for (int i = threadIdx.x; i < np * RP; i += nthr) gSsm[i] = 0.0f;
-  __syncthreads();
-
-  // ---- this warp's entries: rows (b, tile*W + warp, 0..K-1) -------------------------------------
-  const int64_t row0 = ((int64_t)b * prm.n_sub + (int64_t)tile * W + warp) * prm.K;
+    for (int i = threadIdx.x; i < (priv ? W : 1) * K * RP; i += nthr) gCw[i] = 0.0f;
+  }
+  // this warp's entries: rows (b, tile*W + warp, 0..K-1), one contiguous stream
+  const int64_t row0 = ((int64_t)b * prm.n_sub + (int64_t)tile * W + warp) * K;
   const int64_t beg = prm.row_off[row0];
-  const int64_t end = prm.row_off[row0 + prm.K];
+  const int n = (int)(prm.row_off[row0 + K] - beg);
+  int* offs_w = offs + warp * (K + 2);
+  for (int i = lane; i <= K; i += 32) offs_w[i] = (int)(prm.row_off[row0 + i] - beg);
+  if (lane == 0) offs_w[K + 1] = 0x7fffffff;
+  __syncthreads();
+  if (bulk) mbar_wait(&mbar, 0);
+
+  const int32_t* __restrict__ idxw = prm.idx + beg;
+  const uint8_t* __restrict__ lvlw = prm.lvl + beg;
+  float* gCmine = gCw + (priv ? (size_t)warp * K * RP : 0);
 
   float nll_part = 0.0f;
   float acc[RP];
 #pragma unroll
   for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
-  int k_cur = -1;
+  int kcur = 0, cur_off = 0, next_off = offs_w[1];
 
-  auto flush = [&](int kf) {
-    if (kf < 0) return;
-    const float tot = warp_transpose_sum<RP>(acc, lane);
-    const int r_own = warp_transpose_owner<RP>(lane);
-    if ((lane & (32 / RP - 1)) == 0) atomicAdd(gCsm + kf * RP + r_own, tot);
+  int id_n[UNR], lv_n[UNR];
 #pragma unroll
-    for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
-  };
+  for (int j = 0; j < UNR; ++j) {
+    const int pos = 32 * j + lane;
+    id_n[j] = pos < n ? __ldg(idxw + pos) : -1;
+    lv_n[j] = pos < n ? (int)__ldg(lvlw + pos) : 0;
+  }
 
-  for (int64_t base = beg; base < end; base += 32) {
-    const int64_t i = base + lane;
-    const bool valid = i < end;
-    int k = -1, pl = 0, lv = 0;
-    if (valid) {
-      const int id = prm.idx[i];
-      lv = prm.lvl[i];
-      k = fast_div((uint32_t)id, prm.div_magic, prm.div_shift);
-      pl = id - k * prm.IJ - p0;
-    }
-    float s[RP], c[RP];
-    float t = 0.0f;
-    const int kc = valid ? k : 0;
+  for (int pos0 = 0; pos0 < n; pos0 += 32 * UNR) {
+    int id_c[UNR], lv_c[UNR];
 #pragma unroll
-    for (int r = 0; r < RP; ++r) {
-      s[r] = Ssm[pl * RP + r];
-      c[r] = Csm[kc * RP + r];
-      t = fmaf(s[r], c[r], t);
+    for (int j = 0; j < UNR; ++j) {
+      id_c[j] = id_n[j];
+      lv_c[j] = lv_n[j];
+      const int pos = pos0 + 32 * (UNR + j) + lane;  // prefetch the next super-chunk
+      id_n[j] = pos < n ? __ldg(idxw + pos) : -1;
+      lv_n[j] = pos < n ? (int)__ldg(lvlw + pos) : 0;
     }
-    float g = 0.0f;
-    if (valid) {
-      float dxdt;
-      const BinEval ev = eval_entry<EPI, LOGD>(prm, t, lv, dxdt);
-      nll_part -= ev.logp;
-      g = ev.gx * dxdt;
-    }
-    if (GRAD) {
-      // A chunk may straddle band boundaries.  Inside one band the pixels are distinct, so the
-      // lanes of that band update gS without conflicts; bands are handled one after the other.
-      unsigned todo = __ballot_sync(0xffffffffu, valid);
-      while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int kk = __shfl_sync(0xffffffffu, k, leader);
-        const bool mine = valid && k == kk;
-        if (kk != k_cur) {
-          flush(k_cur);
-          k_cur = kk;
+    // ---- phase A: likelihood of UNR independent chunks ------------------------------------------
+    float g[UNR], s[UNR][RP], c[UNR][RP];
+    int pl[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      const bool valid = id_c[j] >= 0;
+      const int id = valid ? id_c[j] : p0;  // (band 0, local pixel 0): harmless stand-in
+      const int k = fast_div((uint32_t)id, prm.div_magic, prm.div_shift);
+      pl[j] = id - k * prm.IJ - p0;
+      float t = 0.0f;
+      if (RP % 4 == 0) {
+#pragma unroll
+        for (int r = 0; r < RP; r += 4) {
+          const float4 sv = *reinterpret_cast<const float4*>(Ssm + pl[j] * RP + r);
+          const float4 cv = *reinterpret_cast<const float4*>(Csm + k * RP + r);
+          s[j][r] = sv.x; s[j][r + 1] = sv.y; s[j][r + 2] = sv.z; s[j][r + 3] = sv.w;
+          c[j][r] = cv.x; c[j][r + 1] = cv.y; c[j][r + 2] = cv.z; c[j][r + 3] = cv.w;
         }
-        if (mine) {
+      } else {
 #pragma unroll
-          for (int r = 0; r < RP; ++r) {
-            gSsm[pl * RP + r] = fmaf(g, c[r], gSsm[pl * RP + r]);
-            acc[r] = fmaf(g, s[r], acc[r]);
+        for (int r = 0; r < RP; ++r) {
+          s[j][r] = Ssm[pl[j] * RP + r];
+          c[j][r] = Csm[k * RP + r];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RP; ++r) t = fmaf(s[j][r], c[j][r], t);
+      float dxdt;
+      const BinEval ev = eval_entry<EPI, LOGD>(prm, t, lv_c[j], dxdt);
+      nll_part -= valid ? ev.logp : 0.0f;
+      g[j] = valid ? ev.gx * dxdt : 0.0f;
+    }
+    if (!GRAD) continue;
+    // ---- phase B: gradient updates, band segment by band segment ---------------------------------
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      const int cstart = pos0 + 32 * j;
+      if (cstart >= n) break;
+      const int cend = min(cstart + 32, n);
+      const int pos = cstart + lane;
+      int seg_start = cstart;
+      while (true) {
+        const int seg_end = min(next_off, cend);
+        if (pos >= seg_start && pos < seg_end) {
+          // lanes of band kcur: distinct pixels, exclusive to this warp
+          if (RP % 4 == 0) {
+#pragma unroll
+            for (int r = 0; r < RP; r += 4) {
+              float4* gp = reinterpret_cast<float4*>(gSsm + pl[j] * RP + r);
+              float4 v = *gp;
+              v.x = fmaf(g[j], c[j][r], v.x); v.y = fmaf(g[j], c[j][r + 1], v.y);
+              v.z = fmaf(g[j], c[j][r + 2], v.z); v.w = fmaf(g[j], c[j][r + 3], v.w);
+              *gp = v;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < RP; ++r) gSsm[pl[j] * RP + r] = fmaf(g[j], c[j][r], gSsm[pl[j] * RP + r]);
           }
+#pragma unroll
+          for (int r = 0; r < RP; ++r) acc[r] = fmaf(g[j], s[j][r], acc[r]);
         }
         __syncwarp();
-        todo &= ~__ballot_sync(0xffffffffu, mine);
+        if (next_off > cend) break;  // band kcur continues in the next chunk
+        // band kcur ends here: reduce its gC contribution across the warp
+        if (next_off > cur_off) {
+          const float tot = warp_transpose_sum<RP>(acc, lane);
+          const int r_own = warp_transpose_owner<RP>(lane);
+          if ((lane & (32 / RP - 1)) == 0) {
+            if (priv) gCmine[kcur * RP + r_own] = tot;
+            else atomicAdd(gCmine + kcur * RP + r_own, tot);
+          }
+#pragma unroll
+          for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
+        }
+        seg_start = seg_end;
+        cur_off = next_off;
+        ++kcur;
+        next_off = offs_w[kcur + 1];
+        if (seg_start >= cend) break;
       }
     }
   }
-  if (GRAD) flush(k_cur);
 
   // ---- NLL ---------------------------------------------------------------------------------------
   double w = warp_sum((double)nll_part);
-  __shared__ double wsum[16];
   if (lane == 0) wsum[warp] = w;
   __syncthreads();  // also orders all gS/gC shared-memory updates before the write-back
   if (threadIdx.x == 0) {
@@ -268,33 +382,34 @@ __global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams pr
 
   // ---- write the gradient tiles back -------------------------------------------------------------
   float* gSb = prm.gS + b * prm.sB;
-  if (prm.sR == 1 && RP == prm.R) {
-    float* dst = gSb + (int64_t)p0 * prm.sP;
-    for (int i = threadIdx.x; i < np * RP; i += nthr) dst[i] = gSsm[i];
+  if (bulk) {
+    fence_async_smem();  // generic-proxy writes to gSsm -> visible to the bulk-copy engine
+    __syncthreads();
+    if (threadIdx.x == 0) bulk_s2g(gSb + (int64_t)p0 * RP, gSsm, (uint32_t)np * RP * sizeof(float));
   } else {
-    for (int i = threadIdx.x; i < np * RP; i += nthr) {
-      const int r = i / np, pl = i - r * np;
-      if (r < prm.R) gSb[r * prm.sR + (int64_t)(p0 + pl) * prm.sP] = gSsm[pl * RP + r];
+#pragma unroll
+    for (int r = 0; r < RP; ++r)
+      if (r < prm.R)
+        for (int pl = threadIdx.x; pl < np; pl += nthr) gSb[r * prm.sR + (int64_t)(p0 + pl) * prm.sP] = gSsm[pl * RP + r];
+  }
+  float* gCb = prm.gC + (int64_t)b * prm.R * K;
+  const int wc = priv ? W : 1;
+#pragma unroll
+  for (int r = 0; r < RP; ++r) {
+    if (r >= prm.R) break;
+    for (int k = threadIdx.x; k < K; k += nthr) {
+      float v = 0.0f;
+      for (int w2 = 0; w2 < wc; ++w2) v += gCw[((size_t)w2 * K + k) * RP + r];
+      if (prm.tiles_per_map == 1) gCb[r * K + k] = v;
+      else atomicAdd(gCb + r * K + k, v);
     }
   }
-  float* gCb = prm.gC + (int64_t)b * prm.R * prm.K;
-  for (int i = threadIdx.x; i < prm.K * RP; i += nthr) {
-    const int r = i / prm.K, k = i - r * prm.K;
-    if (r < prm.R) {
-      if (prm.tiles_per_map == 1) gCb[r * prm.K + k] = gCsm[k * RP + r];
-      else atomicAdd(gCb + r * prm.K + k, gCsm[k * RP + r]);
-    }
-  }
+  if (bulk && threadIdx.x == 0) bulk_wait_all();  // smem must stay alive until the engine has read it
 }
 
 // ------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------
-static size_t tiled_smem_bytes(int K, int RP, int sub_pixels, int W, bool grad) {
-  const size_t TP = (size_t)sub_pixels * W;
-  return ((grad ? 2 : 1) * TP * RP + 2 * (size_t)K * RP) * sizeof(float);
-}
-
 template <int RP, int EPI, bool LOGD, bool GRAD>
 static int launch_one(const GatherParams& prm, int algo, cudaStream_t st) {
   if (algo == QMC_ALGO_FLAT) {
@@ -308,7 +423,8 @@ static int launch_one(const GatherParams& prm, int algo, cudaStream_t st) {
     gather_flat_kernel<RP, EPI, LOGD, GRAD><<<grid, threads, 0, st>>>(prm);
   } else {
     const size_t smem = tiled_smem_bytes(prm.K, RP, prm.sub_pixels, prm.tile_warps, GRAD);
-    auto kern = gather_tiled_kernel<RP, EPI, LOGD, GRAD>;
+    constexpr int UNR = RP <= 4 ? 2 : 1;
+    auto kern = gather_tiled_kernel<RP, EPI, LOGD, GRAD, UNR>;
     QMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ctas = (int64_t)prm.B * prm.tiles_per_map;
     QMC_REQUIRE(ctas <= 0x7fffffff, "too many CTAs (%lld)", (long long)ctas);

@@ -29,7 +29,8 @@ def plan_tiles(IJ: int, K: int, R: int, tile_warps: int = 8, smem_budget: int = 
     RP = 1
     while RP < R:
         RP *= 2
-    fixed = 2 * K * RP * 4
+    wc = tile_warps if tile_warps * K * RP * 4 <= 32 * 1024 else 1     # private gC copies (qmc_gather.cu)
+    fixed = (1 + wc) * K * RP * 4 + tile_warps * (K + 2) * 4 + 16
     max_tile_pixels = max((smem_budget - fixed) // (2 * RP * 4), tile_warps)
     if IJ <= max_tile_pixels:
         sub = -(-IJ // tile_warps)
