@@ -140,6 +140,25 @@ __device__ __forceinline__ BinEval probit_one_sided(float thr, float sgn, float 
   return o;
 }
 
+// Branch-free, SFU-grade form of probit_one_sided for the throughput kernels.  m = -sgn*inv_a
+// (so u = (x - thr)*m); 4 SFU ops (rcp, ex2, lg2, rcp) and no divergence:
+//   u >= 0:  log P = -u^2 + log(erfcx(u)/2),      d log P/du = -(1/sqrt(pi)) / (erfcx(u)/2)
+//   u <  0:  log P = log(1 - e^{-u^2} erfcx|u|/2), d log P/du = -(1/sqrt(pi)) e^{-u^2} / P
+__device__ __forceinline__ BinEval probit_one_sided_fast(float thr, float m, float x) {
+  const float u = (x - thr) * m;
+  const float w = fabsf(u);
+  const float h = 0.5f * erfcx_pos<true>(w);
+  const float w2 = w * w;
+  const float E = ex2_approx(-kLog2e * w2);
+  const bool pos = u >= 0.0f;
+  const float arg = pos ? h : fmaf(-E, h, 1.0f);
+  BinEval o;
+  o.logp = fmaf(lg2_approx(arg), kLn2, pos ? -w2 : 0.0f);
+  // d(-logP)/dx = -dlogp_du * m,  dlogp_du = -(1/sqrt(pi)) * (pos ? 1 : E) / arg
+  o.gx = (kInvSqrtPi * m) * ((pos ? 1.0f : E) * rcp_approx(arg));
+  return o;
+}
+
 // The reference's own arithmetic, literally: F = 0.5*(1+erf(z)), P = F(zu) - F(zl), log P, and
 // the gradient autograd derives from it.  Underflows to P == 0 (log -> -inf, gradient -> inf/NaN)
 // where the reference does.

@@ -48,7 +48,7 @@ __device__ __forceinline__ BinEval eval_entry(const GatherParams& prm, float t, 
     dxdt = 1.0f / u;
   }
   if (EPI == EPI_ONEBIT) {
-    return probit_one_sided<true>(prm.thr, lvl ? 1.0f : -1.0f, x, prm.inv_a);
+    return probit_one_sided_fast(prm.thr, lvl ? -prm.inv_a : prm.inv_a, x);
   } else if (EPI == EPI_REFERENCE) {
     return probit_bin_reference(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
   } else {
@@ -196,12 +196,12 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int RP, int EPI, bool LOGD, bool GRAD, int UNR>
+template <int RP, int EPI, bool LOGD, bool GRAD, int UNR, bool PRIV>
 __global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams prm) {
   extern __shared__ __align__(16) float smem[];
   const int W = prm.tile_warps, K = prm.K;
   const int TP = prm.sub_pixels * W;
-  const bool priv = gc_private(K, RP, W);
+  constexpr bool priv = PRIV;
   float* Ssm = smem;
   float* Csm = Ssm + (size_t)TP * RP;
   float* gSsm = Csm + (size_t)K * RP;
@@ -259,7 +259,9 @@ __global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams pr
 
   const int32_t* __restrict__ idxw = prm.idx + beg;
   const uint8_t* __restrict__ lvlw = prm.lvl + beg;
-  float* gCmine = gCw + (priv ? (size_t)warp * K * RP : 0);
+  float* gCmine = gCw + (PRIV ? (size_t)warp * K * RP : 0);
+  const int IJ = prm.IJ, dshift = prm.div_shift;
+  const uint32_t dmagic = prm.div_magic;
 
   float nll_part = 0.0f;
   float acc[RP];
@@ -267,51 +269,95 @@ __global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams pr
   for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
   int kcur = 0, cur_off = 0, next_off = offs_w[1];
 
-  int id_n[UNR], lv_n[UNR];
+  // gS read-modify-write + gC register accumulation for the lanes selected by `on`
+  auto update = [&](bool on, int pl, float g, const float (&sv)[RP], const float (&cv)[RP]) {
+    if (on) {
+      if (RP % 4 == 0) {
+#pragma unroll
+        for (int r = 0; r < RP; r += 4) {
+          float4* gp = reinterpret_cast<float4*>(gSsm + pl * RP + r);
+          float4 v = *gp;
+          v.x = fmaf(g, cv[r], v.x); v.y = fmaf(g, cv[r + 1], v.y);
+          v.z = fmaf(g, cv[r + 2], v.z); v.w = fmaf(g, cv[r + 3], v.w);
+          *gp = v;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < RP; ++r) gSsm[pl * RP + r] = fmaf(g, cv[r], gSsm[pl * RP + r]);
+      }
+#pragma unroll
+      for (int r = 0; r < RP; ++r) acc[r] = fmaf(g, sv[r], acc[r]);
+    }
+  };
+  // band kcur is complete: reduce its gC contribution across the warp, move to the next band
+  const int r_own = warp_transpose_owner<RP>(lane);
+  const bool writer = (lane & (32 / RP - 1)) == 0;
+  auto end_band = [&]() {
+    if (next_off > cur_off) {  // the band had entries in this sub-tile
+      const float tot = warp_transpose_sum<RP>(acc, lane);
+      if (writer) {
+        if (PRIV) gCmine[kcur * RP + r_own] = tot;
+        else atomicAdd(gCmine + kcur * RP + r_own, tot);
+      }
+#pragma unroll
+      for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
+    }
+    cur_off = next_off;
+    ++kcur;
+    next_off = offs_w[kcur + 1];
+  };
+
+  // two super-chunks of look-ahead: the loads issued in iteration i are consumed in iteration i+2
+  constexpr int SUPER = 32 * UNR;
+  int id_a[UNR], lv_a[UNR], id_b[UNR], lv_b[UNR];
 #pragma unroll
   for (int j = 0; j < UNR; ++j) {
-    const int pos = 32 * j + lane;
-    id_n[j] = pos < n ? __ldg(idxw + pos) : -1;
-    lv_n[j] = pos < n ? (int)__ldg(lvlw + pos) : 0;
+    const int pa = 32 * j + lane, pb = SUPER + 32 * j + lane;
+    id_a[j] = pa < n ? __ldg(idxw + pa) : -1;
+    lv_a[j] = pa < n ? (int)__ldg(lvlw + pa) : 0;
+    id_b[j] = pb < n ? __ldg(idxw + pb) : -1;
+    lv_b[j] = pb < n ? (int)__ldg(lvlw + pb) : 0;
   }
 
-  for (int pos0 = 0; pos0 < n; pos0 += 32 * UNR) {
+  for (int pos0 = 0; pos0 < n; pos0 += SUPER) {
     int id_c[UNR], lv_c[UNR];
 #pragma unroll
     for (int j = 0; j < UNR; ++j) {
-      id_c[j] = id_n[j];
-      lv_c[j] = lv_n[j];
-      const int pos = pos0 + 32 * (UNR + j) + lane;  // prefetch the next super-chunk
-      id_n[j] = pos < n ? __ldg(idxw + pos) : -1;
-      lv_n[j] = pos < n ? (int)__ldg(lvlw + pos) : 0;
+      id_c[j] = id_a[j];
+      lv_c[j] = lv_a[j];
+      id_a[j] = id_b[j];
+      lv_a[j] = lv_b[j];
+      const int pos = pos0 + 2 * SUPER + 32 * j + lane;
+      id_b[j] = pos < n ? __ldg(idxw + pos) : -1;
+      lv_b[j] = pos < n ? (int)__ldg(lvlw + pos) : 0;
     }
     // ---- phase A: likelihood of UNR independent chunks ------------------------------------------
-    float g[UNR], s[UNR][RP], c[UNR][RP];
+    float g[UNR], sv[UNR][RP], cv[UNR][RP];
     int pl[UNR];
 #pragma unroll
     for (int j = 0; j < UNR; ++j) {
       const bool valid = id_c[j] >= 0;
       const int id = valid ? id_c[j] : p0;  // (band 0, local pixel 0): harmless stand-in
-      const int k = fast_div((uint32_t)id, prm.div_magic, prm.div_shift);
-      pl[j] = id - k * prm.IJ - p0;
-      float t = 0.0f;
+      const int k = fast_div((uint32_t)id, dmagic, dshift);
+      pl[j] = id - k * IJ - p0;
       if (RP % 4 == 0) {
 #pragma unroll
         for (int r = 0; r < RP; r += 4) {
-          const float4 sv = *reinterpret_cast<const float4*>(Ssm + pl[j] * RP + r);
-          const float4 cv = *reinterpret_cast<const float4*>(Csm + k * RP + r);
-          s[j][r] = sv.x; s[j][r + 1] = sv.y; s[j][r + 2] = sv.z; s[j][r + 3] = sv.w;
-          c[j][r] = cv.x; c[j][r + 1] = cv.y; c[j][r + 2] = cv.z; c[j][r + 3] = cv.w;
+          const float4 s4 = *reinterpret_cast<const float4*>(Ssm + pl[j] * RP + r);
+          const float4 c4 = *reinterpret_cast<const float4*>(Csm + k * RP + r);
+          sv[j][r] = s4.x; sv[j][r + 1] = s4.y; sv[j][r + 2] = s4.z; sv[j][r + 3] = s4.w;
+          cv[j][r] = c4.x; cv[j][r + 1] = c4.y; cv[j][r + 2] = c4.z; cv[j][r + 3] = c4.w;
         }
       } else {
 #pragma unroll
         for (int r = 0; r < RP; ++r) {
-          s[j][r] = Ssm[pl[j] * RP + r];
-          c[j][r] = Csm[k * RP + r];
+          sv[j][r] = Ssm[pl[j] * RP + r];
+          cv[j][r] = Csm[k * RP + r];
         }
       }
+      float t = 0.0f;
 #pragma unroll
-      for (int r = 0; r < RP; ++r) t = fmaf(s[j][r], c[j][r], t);
+      for (int r = 0; r < RP; ++r) t = fmaf(sv[j][r], cv[j][r], t);
       float dxdt;
       const BinEval ev = eval_entry<EPI, LOGD>(prm, t, lv_c[j], dxdt);
       nll_part -= valid ? ev.logp : 0.0f;
@@ -325,45 +371,22 @@ __global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams pr
       if (cstart >= n) break;
       const int cend = min(cstart + 32, n);
       const int pos = cstart + lane;
-      int seg_start = cstart;
-      while (true) {
-        const int seg_end = min(next_off, cend);
-        if (pos >= seg_start && pos < seg_end) {
-          // lanes of band kcur: distinct pixels, exclusive to this warp
-          if (RP % 4 == 0) {
-#pragma unroll
-            for (int r = 0; r < RP; r += 4) {
-              float4* gp = reinterpret_cast<float4*>(gSsm + pl[j] * RP + r);
-              float4 v = *gp;
-              v.x = fmaf(g[j], c[j][r], v.x); v.y = fmaf(g[j], c[j][r + 1], v.y);
-              v.z = fmaf(g[j], c[j][r + 2], v.z); v.w = fmaf(g[j], c[j][r + 3], v.w);
-              *gp = v;
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < RP; ++r) gSsm[pl[j] * RP + r] = fmaf(g[j], c[j][r], gSsm[pl[j] * RP + r]);
-          }
-#pragma unroll
-          for (int r = 0; r < RP; ++r) acc[r] = fmaf(g[j], s[j][r], acc[r]);
-        }
+      if (next_off >= cend) {
+        // common case: the whole chunk lies in band kcur (distinct pixels, exclusive to this warp)
+        update(pos < cend, pl[j], g[j], sv[j], cv[j]);
         __syncwarp();
-        if (next_off > cend) break;  // band kcur continues in the next chunk
-        // band kcur ends here: reduce its gC contribution across the warp
-        if (next_off > cur_off) {
-          const float tot = warp_transpose_sum<RP>(acc, lane);
-          const int r_own = warp_transpose_owner<RP>(lane);
-          if ((lane & (32 / RP - 1)) == 0) {
-            if (priv) gCmine[kcur * RP + r_own] = tot;
-            else atomicAdd(gCmine + kcur * RP + r_own, tot);
-          }
-#pragma unroll
-          for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
+        if (next_off == cend) end_band();
+      } else {
+        int seg_start = cstart;
+        while (true) {
+          const int seg_end = min(next_off, cend);
+          update(pos >= seg_start && pos < seg_end, pl[j], g[j], sv[j], cv[j]);
+          __syncwarp();
+          if (next_off > cend) break;  // band kcur continues in the next chunk
+          end_band();
+          seg_start = seg_end;
+          if (seg_start >= cend) break;
         }
-        seg_start = seg_end;
-        cur_off = next_off;
-        ++kcur;
-        next_off = offs_w[kcur + 1];
-        if (seg_start >= cend) break;
       }
     }
   }
@@ -424,7 +447,8 @@ static int launch_one(const GatherParams& prm, int algo, cudaStream_t st) {
   } else {
     const size_t smem = tiled_smem_bytes(prm.K, RP, prm.sub_pixels, prm.tile_warps, GRAD);
     constexpr int UNR = RP <= 4 ? 2 : 1;
-    auto kern = gather_tiled_kernel<RP, EPI, LOGD, GRAD, UNR>;
+    auto kern = gc_private(prm.K, RP, prm.tile_warps) ? gather_tiled_kernel<RP, EPI, LOGD, GRAD, UNR, true>
+                                                       : gather_tiled_kernel<RP, EPI, LOGD, GRAD, UNR, false>;
     QMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ctas = (int64_t)prm.B * prm.tiles_per_map;
     QMC_REQUIRE(ctas <= 0x7fffffff, "too many CTAs (%lld)", (long long)ctas);
