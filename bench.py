@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tile-warps", type=int, default=8)
     ap.add_argument("--smem-budget-kb", type=int, default=100)
+    ap.add_argument("--bank-mod", type=int, default=-1, help="-1: conflict-free order for the rank; 0: pixel order")
     ap.add_argument("--layout", default="pixel_major", choices=["pixel_major", "emitter_major"],
                     help="device storage of S for the kernel-only number")
     return ap.parse_args()
@@ -107,7 +108,7 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # workload
 # -------------------------------------------------------------------------------------------------
-def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_budget_kb: int = 100):
+def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_budget_kb: int = 100, bank_mod: int = -1):
     """cfg3 on one GPU: synthetic maps, one-bit observations, tiled compact observation set.
     Seeds: `seed` data, `seed+1` noise and mask."""
     import torch
@@ -138,7 +139,8 @@ def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_bud
     del noisy
     Wx = torch.bernoulli(torch.full(T.shape, c["sampling"], device=device), generator=gen)
     n_sub, sub, tw = q.plan_tiles(IJ, K, R, tile_warps, smem_budget_kb * 1024)
-    obs = q.build_obs(Y, Wx, K, IJ, n_maps, n_sub=n_sub, sub_pixels=sub, tile_warps=tw)
+    obs = q.build_obs(Y, Wx, K, IJ, n_maps, n_sub=n_sub, sub_pixels=sub, tile_warps=tw,
+                      bank_mod=bank_mod if bank_mod >= 0 else q.bank_mod_for_rank(R))
     lik = q.make_likelihood(bb, sigma)
     S_eval = (0.8 * maps.S_true).contiguous()                            # evaluation point
     C_eval = maps.C_true.contiguous()
@@ -244,7 +246,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     from quantized_spectrum_cartography_b200 import _lib
     from quantized_spectrum_cartography_b200._lib import check, lib
 
-    wl = build_workload(args.maps, dev, seed=2 * rank, tile_warps=args.tile_warps, smem_budget_kb=args.smem_budget_kb)
+    wl = build_workload(args.maps, dev, seed=2 * rank, tile_warps=args.tile_warps, smem_budget_kb=args.smem_budget_kb,
+                        bank_mod=args.bank_mod)
     obs, lik, R, K, IJ = wl["obs"], wl["lik"], wl["R"], wl["K"], wl["IJ"]
     B = args.maps
     S = wl["S"]

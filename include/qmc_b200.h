@@ -78,7 +78,7 @@ typedef struct qmc_likelihood {
  * (only Wx != 0 entries contribute, qmc.ipynb c1:150).  Per observed entry a 4-byte linear index
  * idx = k*IJ + p into the reference's [K][IJ] layout and a 1-byte level.  Entries are grouped into
  * rows (map b, pixel sub-tile s, band k) -- sub-tile s covers pixels [s*sub_pixels, (s+1)*sub_pixels)
- * -- in row-major order of (b, s, k), pixels increasing inside a row.  row_off has
+ * -- in row-major order of (b, s, k); the order inside a row is free (see qmc_obs_fill).  row_off has
  * B*n_sub*K + 1 entries.  With n_sub == 1 this is plain band-major order.
  */
 typedef struct qmc_obs_view {
@@ -117,10 +117,13 @@ QMC_API int qmc_quantize_levels(const float* noisy_dev, int64_t n, const float* 
 QMC_API int64_t qmc_obs_scan_ws_elems(int64_t n_rows);
 QMC_API int qmc_obs_count_scan(const float* wx_dev, int B, int K, int IJ, int n_sub, int sub_pixels,
                        int64_t* row_off_dev, int64_t* scan_ws_dev, void* stream);
-/* Pass 2: write idx/lvl in row order.  y is int64 (y_is_int64 != 0, the reference's dtype) or uint8. */
+/* Pass 2: write idx/lvl in row order.  y is int64 (y_is_int64 != 0, the reference's dtype) or uint8.
+ * bank_mod: 0/1 = pixels increasing inside a row; M (power of two <= 32) = entries of a row dealt
+ * round-robin over the residue classes p mod M, which makes the tiled kernel's shared-memory
+ * gathers conflict-free (M = 128 / (4*R_padded)); the kernels accept any order inside a row. */
 QMC_API int qmc_obs_fill(const void* y_dev, int y_is_int64, const float* wx_dev, int B, int K, int IJ,
-                 int n_sub, int sub_pixels, const int64_t* row_off_dev, int32_t* idx_out_dev,
-                 uint8_t* lvl_out_dev, void* stream);
+                 int n_sub, int sub_pixels, int bank_mod, const int64_t* row_off_dev,
+                 int32_t* idx_out_dev, uint8_t* lvl_out_dev, void* stream);
 
 /* ---- a2..a7: fused masked low-rank reconstruction + quantized NLL + factor gradients ---------- */
 

@@ -42,7 +42,7 @@ SIGNATURES = {
     "qmc_quantize_levels": (_I, [_P, _L, C.POINTER(C.c_float), _I, _P, _P, _P]),
     "qmc_obs_scan_ws_elems": (_L, [_L]),
     "qmc_obs_count_scan": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
-    "qmc_obs_fill": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "qmc_obs_fill": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "qmc_nll_fwd_bwd_gather": (_I, [_P, _L, _L, _L, _P, C.POINTER(ObsView), C.POINTER(Likelihood),
                                     _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "qmc_tiled_smem_bytes": (_L, [_I, _I, _I, _I]),

@@ -65,7 +65,7 @@ __device__ __forceinline__ float q_rcp(float x) {
   return FAST ? rcp_approx(x) : 1.0f / x;
 }
 
-// erfcx(w) = exp(w^2) erfc(w) for w >= 0 (w = +inf gives 0).  One reciprocal and a degree-10
+// erfcx(w) = exp(w^2) erfc(w) for w >= 0 (w = +inf gives 0).  One reciprocal and a low-degree
 // Horner chain; see gen_erfcx_coeffs.py for the derivation and the measured error.
 template <bool FAST>
 __device__ __forceinline__ float erfcx_pos(float w) {

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) gather_flat_kernel(const GatherParams prm
 // One CTA per (map, pixel tile), tile_warps warps; warp w owns pixel sub-tile (tile*W + w) exclusively
 // and walks its entries -- one contiguous stream, rows (bands) in increasing order -- 32*UNR at a
 // time.  Shared memory (floats):
-//   Ssm[TP][RP] | gSsm[TP][RP] | Csm[K][RP] | gCw[Wc][K][RP] | offs[W][K+2] (int)
+//   Ssm[TP][RP] | Csm[K][RP] | gSsm[TP][RP] | gCw[Wc][K][RP] | scratch[W][32][RP] | offs[W][K+2] (int)
 // TP = tile pixels.  gCw holds one private copy of gC per warp (Wc = W) when that fits, otherwise a
 // single copy updated with shared-memory atomics (Wc = 1).
 //
@@ -162,6 +162,7 @@ static size_t tiled_smem_bytes(int K, int RP, int sub_pixels, int W, bool grad) 
   const size_t wc = gc_private(K, RP, W) ? W : 1;
   size_t fl = TP * RP + (size_t)K * RP;
   if (grad) fl += TP * RP + wc * K * RP;
+  if (grad) fl += (size_t)W * 32 * RP;  // per-lane scratch rows for masked-off updates
   return fl * sizeof(float) + (size_t)W * (K + 2) * sizeof(int) + 16;
 }
 
@@ -196,8 +197,41 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic in the loop) --
+// read-only data of the main loop (S and C tiles): plain asm, free to be scheduled
+__device__ __forceinline__ float4 lds128_ro(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32_ro(uint32_t a) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+// read-modify-write data (gradient tiles): ordered
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ int lds32i(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+
 template <int RP, int EPI, bool LOGD, bool GRAD, int UNR, bool PRIV>
-__global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams prm) {
+__global__ void __launch_bounds__(256, 2) gather_tiled_kernel(const GatherParams prm) {
   extern __shared__ __align__(16) float smem[];
   const int W = prm.tile_warps, K = prm.K;
   const int TP = prm.sub_pixels * W;
@@ -206,7 +240,8 @@ __global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams pr
   float* Csm = Ssm + (size_t)TP * RP;
   float* gSsm = Csm + (size_t)K * RP;
   float* gCw = gSsm + (GRAD ? (size_t)TP * RP : 0);
-  int* offs = reinterpret_cast<int*>(gCw + (GRAD ? (size_t)(priv ? W : 1) * K * RP : 0));
+  float* scratch = gCw + (GRAD ? (size_t)(priv ? W : 1) * K * RP : 0);
+  int* offs = reinterpret_cast<int*>(scratch + (GRAD ? (size_t)W * 32 * RP : 0));
   __shared__ uint64_t mbar;
   __shared__ double wsum[16];
 
@@ -267,59 +302,69 @@ __global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams pr
   float acc[RP];
 #pragma unroll
   for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
-  int kcur = 0, cur_off = 0, next_off = offs_w[1];
+  int cur_off = 0, next_off = offs_w[1];  // rows [cur_off, next_off) = current band
 
-  // gS read-modify-write + gC register accumulation for the lanes selected by `on`
-  auto update = [&](bool on, int pl, float g, const float (&sv)[RP], const float (&cv)[RP]) {
-    if (on) {
-      if (RP % 4 == 0) {
+  // shared addresses used in the loop
+  constexpr uint32_t ROWB = RP * sizeof(float);  // bytes per pixel row / band row
+  const uint32_t S_a = smem_u32(Ssm), C_a = smem_u32(Csm);
+  const uint32_t gS_delta = smem_u32(gSsm) - S_a;  // gS row address = S row address + delta
+  const uint32_t scr_a = smem_u32(scratch) + (uint32_t)(warp * 32 + lane) * ROWB;
+
+  // gS read-modify-write + gC register accumulation for the lanes selected by `on`.  Straight-line:
+  // masked-off lanes update a private scratch row with g = 0 instead of branching around the code.
+  auto update = [&](bool on, uint32_t s_row, float g, const float (&sv)[RP], const float (&cv)[RP]) {
+    const uint32_t row = on ? s_row + gS_delta : scr_a;
+    const float ge = on ? g : 0.0f;
+    if (RP % 4 == 0) {
 #pragma unroll
-        for (int r = 0; r < RP; r += 4) {
-          float4* gp = reinterpret_cast<float4*>(gSsm + pl * RP + r);
-          float4 v = *gp;
-          v.x = fmaf(g, cv[r], v.x); v.y = fmaf(g, cv[r + 1], v.y);
-          v.z = fmaf(g, cv[r + 2], v.z); v.w = fmaf(g, cv[r + 3], v.w);
-          *gp = v;
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < RP; ++r) gSsm[pl * RP + r] = fmaf(g, cv[r], gSsm[pl * RP + r]);
+      for (int r = 0; r < RP; r += 4) {
+        float4 v = lds128(row + r * 4);
+        v.x = fmaf(ge, cv[r], v.x); v.y = fmaf(ge, cv[r + 1], v.y);
+        v.z = fmaf(ge, cv[r + 2], v.z); v.w = fmaf(ge, cv[r + 3], v.w);
+        sts128(row + r * 4, v);
       }
+    } else {
 #pragma unroll
-      for (int r = 0; r < RP; ++r) acc[r] = fmaf(g, sv[r], acc[r]);
+      for (int r = 0; r < RP; ++r) sts32(row + r * 4, fmaf(ge, cv[r], lds32(row + r * 4)));
     }
+#pragma unroll
+    for (int r = 0; r < RP; ++r) acc[r] = fmaf(ge, sv[r], acc[r]);
   };
   // band kcur is complete: reduce its gC contribution across the warp, move to the next band
-  const int r_own = warp_transpose_owner<RP>(lane);
   const bool writer = (lane & (32 / RP - 1)) == 0;
+  uint32_t gc_a = smem_u32(gCmine + warp_transpose_owner<RP>(lane));  // advances by one band row per band
+  uint32_t off_a = smem_u32(offs_w + 2);                              // &offs_w[kcur + 2]
   auto end_band = [&]() {
     if (next_off > cur_off) {  // the band had entries in this sub-tile
       const float tot = warp_transpose_sum<RP>(acc, lane);
       if (writer) {
-        if (PRIV) gCmine[kcur * RP + r_own] = tot;
-        else atomicAdd(gCmine + kcur * RP + r_own, tot);
+        if (PRIV) sts32(gc_a, tot);
+        else atomicAdd(gCmine + (gc_a - smem_u32(gCmine)) / 4, tot);
       }
 #pragma unroll
       for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
     }
     cur_off = next_off;
-    ++kcur;
-    next_off = offs_w[kcur + 1];
+    gc_a += ROWB;
+    next_off = lds32i(off_a);
+    off_a += 4;
   };
 
   // two super-chunks of look-ahead: the loads issued in iteration i are consumed in iteration i+2
   constexpr int SUPER = 32 * UNR;
   int id_a[UNR], lv_a[UNR], id_b[UNR], lv_b[UNR];
+  const int32_t* ip = idxw + lane;   // running per-lane pointers: loads use immediate offsets
+  const uint8_t* lp = lvlw + lane;
+  int rem = n - lane;                 // entries left from this lane's position
 #pragma unroll
   for (int j = 0; j < UNR; ++j) {
-    const int pa = 32 * j + lane, pb = SUPER + 32 * j + lane;
-    id_a[j] = pa < n ? __ldg(idxw + pa) : -1;
-    lv_a[j] = pa < n ? (int)__ldg(lvlw + pa) : 0;
-    id_b[j] = pb < n ? __ldg(idxw + pb) : -1;
-    lv_b[j] = pb < n ? (int)__ldg(lvlw + pb) : 0;
+    id_a[j] = 32 * j < rem ? __ldg(ip + 32 * j) : -1;
+    lv_a[j] = 32 * j < rem ? (int)__ldg(lp + 32 * j) : 0;
+    id_b[j] = SUPER + 32 * j < rem ? __ldg(ip + SUPER + 32 * j) : -1;
+    lv_b[j] = SUPER + 32 * j < rem ? (int)__ldg(lp + SUPER + 32 * j) : 0;
   }
 
-  for (int pos0 = 0; pos0 < n; pos0 += SUPER) {
+  for (int pos0 = 0; pos0 < n; pos0 += SUPER, ip += SUPER, lp += SUPER, rem -= SUPER) {
     int id_c[UNR], lv_c[UNR];
 #pragma unroll
     for (int j = 0; j < UNR; ++j) {
@@ -327,32 +372,33 @@ __global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams pr
       lv_c[j] = lv_a[j];
       id_a[j] = id_b[j];
       lv_a[j] = lv_b[j];
-      const int pos = pos0 + 2 * SUPER + 32 * j + lane;
-      id_b[j] = pos < n ? __ldg(idxw + pos) : -1;
-      lv_b[j] = pos < n ? (int)__ldg(lvlw + pos) : 0;
+      const bool more = 2 * SUPER + 32 * j < rem;
+      id_b[j] = more ? __ldg(ip + 2 * SUPER + 32 * j) : -1;
+      lv_b[j] = more ? (int)__ldg(lp + 2 * SUPER + 32 * j) : 0;
     }
     // ---- phase A: likelihood of UNR independent chunks ------------------------------------------
     float g[UNR], sv[UNR][RP], cv[UNR][RP];
-    int pl[UNR];
+    uint32_t srow[UNR];
 #pragma unroll
     for (int j = 0; j < UNR; ++j) {
       const bool valid = id_c[j] >= 0;
       const int id = valid ? id_c[j] : p0;  // (band 0, local pixel 0): harmless stand-in
       const int k = fast_div((uint32_t)id, dmagic, dshift);
-      pl[j] = id - k * IJ - p0;
+      srow[j] = S_a + (uint32_t)(id - k * IJ - p0) * ROWB;
+      const uint32_t crow = C_a + (uint32_t)k * ROWB;
       if (RP % 4 == 0) {
 #pragma unroll
         for (int r = 0; r < RP; r += 4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(Ssm + pl[j] * RP + r);
-          const float4 c4 = *reinterpret_cast<const float4*>(Csm + k * RP + r);
+          const float4 s4 = lds128_ro(srow[j] + r * 4);
+          const float4 c4 = lds128_ro(crow + r * 4);
           sv[j][r] = s4.x; sv[j][r + 1] = s4.y; sv[j][r + 2] = s4.z; sv[j][r + 3] = s4.w;
           cv[j][r] = c4.x; cv[j][r + 1] = c4.y; cv[j][r + 2] = c4.z; cv[j][r + 3] = c4.w;
         }
       } else {
 #pragma unroll
         for (int r = 0; r < RP; ++r) {
-          sv[j][r] = Ssm[pl[j] * RP + r];
-          cv[j][r] = Csm[k * RP + r];
+          sv[j][r] = lds32_ro(srow[j] + r * 4);
+          cv[j][r] = lds32_ro(crow + r * 4);
         }
       }
       float t = 0.0f;
@@ -371,23 +417,27 @@ __global__ void __launch_bounds__(512) gather_tiled_kernel(const GatherParams pr
       if (cstart >= n) break;
       const int cend = min(cstart + 32, n);
       const int pos = cstart + lane;
+      const bool valid = pos < cend;
       if (next_off >= cend) {
-        // common case: the whole chunk lies in band kcur (distinct pixels, exclusive to this warp)
-        update(pos < cend, pl[j], g[j], sv[j], cv[j]);
-        __syncwarp();
+        // the whole chunk lies in the current band (distinct pixels, exclusive to this warp)
+        update(valid, srow[j], g[j], sv[j], cv[j]);
         if (next_off == cend) end_band();
       } else {
-        int seg_start = cstart;
-        while (true) {
-          const int seg_end = min(next_off, cend);
-          update(pos >= seg_start && pos < seg_end, pl[j], g[j], sv[j], cv[j]);
+        // a band ends inside the chunk: its lanes first, then the rest
+        int bnd = next_off;
+        update(pos < bnd, srow[j], g[j], sv[j], cv[j]);
+        __syncwarp();
+        end_band();
+        while (next_off < cend) {  // (rare) further whole bands inside this chunk
+          update(pos >= bnd && pos < next_off, srow[j], g[j], sv[j], cv[j]);
           __syncwarp();
-          if (next_off > cend) break;  // band kcur continues in the next chunk
+          bnd = next_off;
           end_band();
-          seg_start = seg_end;
-          if (seg_start >= cend) break;
         }
+        update(pos >= bnd && valid, srow[j], g[j], sv[j], cv[j]);
+        if (next_off == cend) end_band();
       }
+      __syncwarp();
     }
   }
 
@@ -479,7 +529,7 @@ static int launch_rp(const GatherParams& prm, int algo, int epi, bool logd, bool
 using namespace qmc;
 
 extern "C" int64_t qmc_tiled_smem_bytes(int K, int R, int sub_pixels, int tile_warps) {
-  if (K <= 0 || R <= 0 || R > QMC_MAX_RANK || sub_pixels <= 0 || tile_warps <= 0 || tile_warps > 16) return 0;
+  if (K <= 0 || R <= 0 || R > QMC_MAX_RANK || sub_pixels <= 0 || tile_warps <= 0 || tile_warps > 8) return 0;
   int RP = 1;
   while (RP < R) RP <<= 1;
   const size_t b = tiled_smem_bytes(K, RP, sub_pixels, tile_warps, true);
@@ -545,7 +595,7 @@ extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, in
                ? QMC_ALGO_TILED : QMC_ALGO_FLAT;
   }
   if (algo == QMC_ALGO_TILED) {
-    QMC_REQUIRE(tile_warps > 0 && tile_warps <= 16, "tile_warps %d out of range", tile_warps);
+    QMC_REQUIRE(tile_warps > 0 && tile_warps <= 8, "tile_warps %d out of range [1, 8]", tile_warps);
     QMC_REQUIRE(obs->n_sub % tile_warps == 0, "n_sub %d is not a multiple of tile_warps %d", obs->n_sub, tile_warps);
     QMC_REQUIRE(tiled_smem_bytes(K, RP, obs->sub_pixels, tile_warps, grad) <= 227 * 1024,
                 "tile of %d pixels x rank %d does not fit shared memory", obs->sub_pixels * tile_warps, RP);

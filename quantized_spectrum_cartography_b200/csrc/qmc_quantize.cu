@@ -63,10 +63,16 @@ __global__ void obs_count_kernel(const float* __restrict__ wx, int64_t n_rows, i
   if (lane == 0) counts[row] = cnt;
 }
 
+// Order of the entries inside a row.  bank_mod <= 1: increasing pixel.  bank_mod = M > 1: the
+// shared-memory-friendly order used by the tiled kernel -- entries are dealt round-robin over the
+// residue classes c = p mod M (level t holds the t-th entry of every class that has one, classes in
+// increasing order), so that any M consecutive entries of a row touch M different bank groups when
+// the kernel gathers the [pixel][R] rows of S / gS.  Within a row the kernel is order-agnostic.
 template <typename YT>
 __global__ void obs_fill_kernel(const YT* __restrict__ y, const float* __restrict__ wx, int64_t n_rows,
-                                int K, int IJ, int n_sub, int SP, const int64_t* __restrict__ row_off,
-                                int32_t* __restrict__ idx, uint8_t* __restrict__ lvl) {
+                                int K, int IJ, int n_sub, int SP, int bank_mod,
+                                const int64_t* __restrict__ row_off, int32_t* __restrict__ idx,
+                                uint8_t* __restrict__ lvl) {
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_rows) return;
@@ -76,17 +82,66 @@ __global__ void obs_fill_kernel(const YT* __restrict__ y, const float* __restric
   const int64_t b = bs / n_sub;
   const int pb = s * SP, pe = min(pb + SP, IJ);
   const int64_t plane = ((int64_t)b * K + k) * IJ;
-  int64_t out = row_off[row];
+  const int64_t out0 = row_off[row];
+  if (bank_mod <= 1) {
+    int64_t out = out0;
+    for (int p0 = pb; p0 < pe; p0 += 32) {
+      const int p = p0 + lane;
+      const bool on = p < pe && (!wx || wx[plane + p] != 0.0f);
+      const unsigned m = __ballot_sync(0xffffffffu, on);
+      if (on) {
+        const int64_t o = out + __popc(m & ((1u << lane) - 1u));
+        idx[o] = k * IJ + p;
+        lvl[o] = (uint8_t)y[plane + p];
+      }
+      out += __popc(m);
+    }
+    return;
+  }
+  // pass 1: class sizes.  Lane c (c < M) keeps the running count of class c.
+  const int M = bank_mod;  // power of two <= 32
+  int cnt = 0;
   for (int p0 = pb; p0 < pe; p0 += 32) {
     const int p = p0 + lane;
     const bool on = p < pe && (!wx || wx[plane + p] != 0.0f);
     const unsigned m = __ballot_sync(0xffffffffu, on);
+    // lanes whose pixel has residue `lane` (for lane < M): l with (p0 + l) % M == lane
+    unsigned cls = 0;
+    if (lane < M) {
+      const int first = ((lane - p0) % M + M) % M;
+      for (int l = first; l < 32; l += M) cls |= 1u << l;
+    }
+    cnt += __popc(m & cls);
+  }
+  // pass 2: position = #entries in lower levels + #lower classes present in my level
+  int seen = 0;  // lane c: entries of class c placed so far
+  for (int p0 = pb; p0 < pe; p0 += 32) {
+    const int p = p0 + lane;
+    const bool on = p < pe && (!wx || wx[plane + p] != 0.0f);
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    const int c = p & (M - 1);
+    unsigned same = 0;  // lanes of this chunk with my residue
+    {
+      const int first = lane & (M - 1);
+      for (int l = first; l < 32; l += M) same |= 1u << l;
+    }
+    const int rank = __shfl_sync(0xffffffffu, seen, c) + __popc(m & same & ((1u << lane) - 1u));
+    int pos = 0;
+    for (int c2 = 0; c2 < M; ++c2) {
+      const int n2 = __shfl_sync(0xffffffffu, cnt, c2);
+      pos += min(n2, rank) + ((c2 < c && n2 > rank) ? 1 : 0);
+    }
     if (on) {
-      const int64_t o = out + __popc(m & ((1u << lane) - 1u));
+      const int64_t o = out0 + pos;
       idx[o] = k * IJ + p;
       lvl[o] = (uint8_t)y[plane + p];
     }
-    out += __popc(m);
+    unsigned cls = 0;
+    if (lane < M) {
+      const int first = ((lane - p0) % M + M) % M;
+      for (int l = first; l < 32; l += M) cls |= 1u << l;
+    }
+    seen += __popc(m & cls);
   }
 }
 
@@ -222,8 +277,9 @@ extern "C" int qmc_obs_count_scan(const float* wx_dev, int B, int K, int IJ, int
 }
 
 extern "C" int qmc_obs_fill(const void* y_dev, int y_is_int64, const float* wx_dev, int B, int K, int IJ,
-                            int n_sub, int sub_pixels, const int64_t* row_off_dev, int32_t* idx_out_dev,
-                            uint8_t* lvl_out_dev, void* stream) {
+                            int n_sub, int sub_pixels, int bank_mod, const int64_t* row_off_dev,
+                            int32_t* idx_out_dev, uint8_t* lvl_out_dev, void* stream) {
+  QMC_REQUIRE(bank_mod >= 0 && bank_mod <= 32 && (bank_mod & (bank_mod - 1)) == 0, "bank_mod %d must be 0 or a power of two <= 32", bank_mod);
   QMC_REQUIRE(y_dev && row_off_dev && idx_out_dev && lvl_out_dev, "null argument");
   QMC_REQUIRE(B > 0 && K > 0 && IJ > 0 && n_sub > 0 && sub_pixels > 0, "bad sizes");
   QMC_REQUIRE((int64_t)K * IJ < (1LL << 31), "K*IJ does not fit the int32 linear index");
@@ -233,10 +289,10 @@ extern "C" int qmc_obs_fill(const void* y_dev, int y_is_int64, const float* wx_d
   QMC_REQUIRE(blocks <= 0x7fffffff, "too many rows");
   if (y_is_int64)
     obs_fill_kernel<int64_t><<<(unsigned)blocks, 256, 0, st>>>((const int64_t*)y_dev, wx_dev, n_rows, K, IJ, n_sub,
-                                                               sub_pixels, row_off_dev, idx_out_dev, lvl_out_dev);
+                                                               sub_pixels, bank_mod, row_off_dev, idx_out_dev, lvl_out_dev);
   else
     obs_fill_kernel<uint8_t><<<(unsigned)blocks, 256, 0, st>>>((const uint8_t*)y_dev, wx_dev, n_rows, K, IJ, n_sub,
-                                                               sub_pixels, row_off_dev, idx_out_dev, lvl_out_dev);
+                                                               sub_pixels, bank_mod, row_off_dev, idx_out_dev, lvl_out_dev);
   count_launch();
   QMC_CUDA_CHECK(cudaGetLastError());
   return QMC_OK;

@@ -22,7 +22,7 @@ import torch
 
 from . import _lib
 from ._lib import Likelihood, check, lib
-from .obs import ObsSet, build_obs, plan_tiles
+from .obs import ObsSet, bank_mod_for_rank, build_obs, plan_tiles
 
 REF_SENTINEL = 100000.0  # quantization_model.py:32-33
 
@@ -195,7 +195,8 @@ def make_obs(Y, Wx, K: Optional[int] = None, device=None, *, B: int = 1, R: Opti
         if R is None:
             raise ValueError("tiled layout needs R")
         n_sub, sub, tw = plan_tiles(IJ, K, R, tile_warps)
+        bm = bank_mod_for_rank(R)
     else:
-        n_sub, sub, tw = 1, IJ, 0
+        n_sub, sub, tw, bm = 1, IJ, 0, 0
     return build_obs(Y.to(dev), None if Wx is None else Wx.to(dev), K, IJ, B, n_sub=n_sub, sub_pixels=sub,
-                     tile_warps=tw)
+                     tile_warps=tw, bank_mod=bm)

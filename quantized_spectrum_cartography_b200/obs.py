@@ -30,7 +30,7 @@ def plan_tiles(IJ: int, K: int, R: int, tile_warps: int = 8, smem_budget: int = 
     while RP < R:
         RP *= 2
     wc = tile_warps if tile_warps * K * RP * 4 <= 32 * 1024 else 1     # private gC copies (qmc_gather.cu)
-    fixed = (1 + wc) * K * RP * 4 + tile_warps * (K + 2) * 4 + 16
+    fixed = (1 + wc) * K * RP * 4 + tile_warps * (K + 2) * 4 + tile_warps * 32 * RP * 4 + 16
     max_tile_pixels = max((smem_budget - fixed) // (2 * RP * 4), tile_warps)
     if IJ <= max_tile_pixels:
         sub = -(-IJ // tile_warps)
@@ -74,8 +74,17 @@ class ObsSet:
         return self.nobs * 5 + self.B * (2 * 4 * R * (self.IJ + self.K) + 4)
 
 
+def bank_mod_for_rank(R: int) -> int:
+    """Residue modulus that makes the tiled kernel's gathers of [pixel][R_padded] fp32 rows
+    conflict-free: rows of 4*R_padded bytes, 128 bytes served per shared-memory wavefront."""
+    RP = 1
+    while RP < R:
+        RP *= 2
+    return max(128 // (4 * RP), 1)
+
+
 def build_obs(Y: torch.Tensor, Wx: torch.Tensor | None, K: int, IJ: int, B: int = 1, *,
-              n_sub: int = 1, sub_pixels: int | None = None, tile_warps: int = 0) -> ObsSet:
+              n_sub: int = 1, sub_pixels: int | None = None, tile_warps: int = 0, bank_mod: int = 0) -> ObsSet:
     """(Y, Wx) dense ``[B][K][IJ]`` (any shape with that many elements; the reference's is
     ``[K,1,I,J]``) -> ObsSet on Y's CUDA device.  Y: int64 (reference dtype) or uint8."""
     if not Y.is_cuda:
@@ -103,7 +112,7 @@ def build_obs(Y: torch.Tensor, Wx: torch.Tensor | None, K: int, IJ: int, B: int 
         idx = torch.empty(max(nobs, 1), dtype=torch.int32, device=dev)
         lvl = torch.empty(max(nobs, 1), dtype=torch.uint8, device=dev)
         check(lib.qmc_obs_fill(Yc.data_ptr(), int(Y.dtype == torch.int64), wptr, B, K, IJ, n_sub, sub_pixels,
-                               row_off.data_ptr(), idx.data_ptr(), lvl.data_ptr(), _stream()))
+                               bank_mod, row_off.data_ptr(), idx.data_ptr(), lvl.data_ptr(), _stream()))
         max_level = int(lvl[:nobs].max().item()) if nobs else 0
     return ObsSet(idx[:nobs] if nobs else idx[:0], lvl[:nobs] if nobs else lvl[:0], row_off, B, K, IJ,
                   n_sub, sub_pixels, tile_warps, nobs, max_level)

@@ -45,8 +45,8 @@ def test_argument_validation_needs_no_gpu():
     assert rc == 1 and b"bad arguments" in _lib.lib.qmc_last_error()
     with pytest.raises(_lib.QmcError):
         _lib.check(rc)
-    # cfg1/cfg3 tile: S + gS tiles, C, 8 private gC copies, 8 x (K+2) row offsets
-    assert _lib.lib.qmc_tiled_smem_bytes(64, 4, 326, 8) == (2 * 326 * 8 * 4 + 9 * 64 * 4) * 4 + 8 * 66 * 4 + 16
+    # cfg1/cfg3 tile: S + gS tiles, C, 8 private gC copies, 8 x 32 scratch rows, 8 x (K+2) row offsets
+    assert _lib.lib.qmc_tiled_smem_bytes(64, 4, 326, 8) == (2 * 326 * 8 * 4 + 9 * 64 * 4 + 8 * 32 * 4) * 4 + 8 * 66 * 4 + 16
     assert _lib.lib.qmc_tiled_smem_bytes(64, 4, 100000, 8) == 0
 
 

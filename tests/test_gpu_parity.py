@@ -86,13 +86,13 @@ def test_device_side_noisy_signal_is_bit_exact(q):
             assert (out.cpu() - want).abs().max() <= 2e-6
 
 
-@pytest.mark.parametrize("n_sub,sub", [(1, None), (8, 326), (3, 900)])
-def test_obs_builder_matches_mask_semantics(q, nll_golden, n_sub, sub):
+@pytest.mark.parametrize("n_sub,sub,bank_mod", [(1, None, 0), (8, 326, 0), (3, 900, 0), (8, 326, 8), (2, 1400, 4), (1, None, 32)])
+def test_obs_builder_matches_mask_semantics(q, nll_golden, n_sub, sub, bank_mod):
     g = nll_golden["g"]
     Wx = nll_golden["Wx"]
     Y = torch.from_numpy(g["lin8u_s2bw__Y"].astype(np.int64)).unsqueeze(1)
     K, IJ = 64, 2601
-    obs = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, 1, n_sub=n_sub, sub_pixels=sub)
+    obs = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, 1, n_sub=n_sub, sub_pixels=sub, bank_mod=bank_mod)
     idx_ref, lvl_ref = oc.observed_entries(Y, Wx)
     assert obs.nobs == idx_ref.size
     idx = obs.idx.cpu().numpy().astype(np.int64)
@@ -109,10 +109,26 @@ def test_obs_builder_matches_mask_semantics(q, nll_golden, n_sub, sub):
     rows = (p // sp) * K + k
     assert np.all(np.diff(rows) >= 0)
     same = np.diff(rows) == 0
-    assert np.all(np.diff(p)[same] > 0)
     np.testing.assert_array_equal(np.bincount(rows, minlength=obs.n_sub * K), np.diff(ro))
+    if bank_mod <= 1:
+        assert np.all(np.diff(p)[same] > 0)                 # pixels increasing inside a row
+    else:
+        # round-robin over residue classes p mod M: inside a row, entry j has the (j-th smallest)
+        # (rank-in-class, class) key, so any M consecutive entries drawn from full levels are distinct
+        M = bank_mod
+        bad = total = 0
+        for r in np.flatnonzero(np.diff(ro) >= 2 * M)[:200]:
+            seg = p[ro[r]:ro[r + 1]]
+            cls = seg % M
+            cnt = np.bincount(cls, minlength=M)
+            full = cnt.min() * M                             # entries in levels that contain every class
+            assert sorted(seg.tolist()) == sorted(set(seg.tolist()))
+            for a in range(0, full - M + 1):
+                total += 1
+                bad += len(set(cls[a:a + M].tolist())) != M
+        assert total > 0 and bad == 0
     # uint8 levels and "everything observed" are accepted too
-    obs8 = q.build_obs(Y.to(torch.uint8).cuda(), None, K, IJ, 1, n_sub=n_sub, sub_pixels=sub)
+    obs8 = q.build_obs(Y.to(torch.uint8).cuda(), None, K, IJ, 1, n_sub=n_sub, sub_pixels=sub, bank_mod=bank_mod)
     assert obs8.nobs == K * IJ
 
 
@@ -198,7 +214,8 @@ def test_batched_maps_match_oracle_per_map(q, R, levels, log_domain, algo):
         n_sub, sub, tw = 4, -(-I * J // 4), 2   # two tiles of two warps each: exercises the cross-tile gC reduction
     else:
         n_sub, sub, tw = 1, I * J, 0
-    obs = q.build_obs(Y.cuda(), Wx.cuda(), K, I * J, B, n_sub=n_sub, sub_pixels=sub, tile_warps=tw)
+    obs = q.build_obs(Y.cuda(), Wx.cuda(), K, I * J, B, n_sub=n_sub, sub_pixels=sub, tile_warps=tw,
+                      bank_mod=q.bank_mod_for_rank(R) if algo == "tiled" else 0)
     nll, gS, gC = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik,
                                 algo=_lib.QMC_ALGO_TILED if algo == "tiled" else _lib.QMC_ALGO_FLAT)
     for b in range(B):
@@ -224,7 +241,8 @@ def test_tiled_kernel_pixel_major_storage_and_full_size_map(q):
     S, C, Y, Wx, bb, sigma, off = _random_instance(B, I, J, K, R, 0.1, 2, seed=42)
     lik = q.make_likelihood(bb, sigma)
     n_sub, sub, tw = q.plan_tiles(I * J, K, R)
-    obs_t = q.build_obs(Y.cuda(), Wx.cuda(), K, I * J, B, n_sub=n_sub, sub_pixels=sub, tile_warps=tw)
+    obs_t = q.build_obs(Y.cuda(), Wx.cuda(), K, I * J, B, n_sub=n_sub, sub_pixels=sub, tile_warps=tw,
+                        bank_mod=q.bank_mod_for_rank(R))
     obs_f = q.build_obs(Y.cuda(), Wx.cuda(), K, I * J, B)
     S_pm = S.cuda().transpose(1, 2).contiguous().transpose(1, 2)      # [B,R,IJ] view of [B,IJ,R] storage
     assert S_pm.stride() == (R * I * J, 1, R)
