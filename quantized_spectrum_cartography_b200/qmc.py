@@ -1,0 +1,181 @@
+"""QMC maximum-likelihood solver: alternating Adam on the factors with the fused likelihood op.
+
+The reference's ``qmc/qmc.py`` is a 29-line setup stub; its actual solver lives in the notebook
+``qmc/qmc.ipynb`` cell 1 (:136-229), and the pure low-rank variant (S optimised directly, no
+generator) in ``backup/notebooks/onebit_lowrank.ipynb`` cell 1.  This module restates that loop for
+B independent maps at once:
+
+    repeat:
+        C-step:  cost = nll(S.detach(), C) + lam_c * ||C||_F     -> Adam(lr_c) on C     (c1:140-154)
+                 C[C < 0] = 0                                                           (c1:156-157)
+        S-step:  cost = nll(S, C.detach()) + lam_s * ||S||_F     -> Adam(lr_s) on S     (c1:199-212,
+                 S[S < 0] = 0                                       with S in place of generator(Z))
+        track cost and NMSE(get_tensor(S, C), T_true)                                   (c1:214-217)
+
+``nll`` is one fused CUDA launch per evaluation (:func:`..fused.qmc_nll_batched`); the norms are
+non-squared Frobenius norms per map exactly as in the notebook (their sub-gradient at 0 is 0).  The
+likelihood backend is injectable only so that the parity test can drive the same loop with the
+checker; the default and only product backend is the CUDA kernel.
+
+CLI:  python -m quantized_spectrum_cartography_b200.qmc --config cfg1|cfg2 [--maps B] [--iters N]
+"""
+from __future__ import annotations
+
+import argparse
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Optional
+
+import torch
+
+
+@dataclass
+class SolverConfig:
+    iters: int = 500            # maxIter, c1:41
+    lr_c: float = 0.005         # c1:126
+    lr_s: float = 0.001
+    lam_c: float = 100.0        # c1:51
+    lam_s: float = 100.0        # c1:52
+    c_inner: int = 1            # cinnerIter, c1:62
+    s_inner: int = 1            # sinnerIter, c1:63
+    project_c: bool = True      # c1:156-157
+    project_s: bool = True
+    track_every: int = 1        # the notebook evaluates NMSE every iteration (a host sync each time)
+
+
+@dataclass
+class SolverResult:
+    S: torch.Tensor             # [B, R, IJ]
+    C: torch.Tensor             # [B, R, K]
+    cost: list = field(default_factory=list)   # per tracked iteration: [B] tensors (last S-step cost)
+    nmse: list = field(default_factory=list)
+    seconds: float = 0.0
+    iterations: int = 0
+
+
+def _frob(x: torch.Tensor) -> torch.Tensor:
+    """Per-map non-squared Frobenius norm (torch.norm(., 'fro') of the notebook, one per map)."""
+    return torch.linalg.vector_norm(x.reshape(x.shape[0], -1), dim=1)
+
+
+def solve_lowrank(S0: torch.Tensor, C0: torch.Tensor, nll_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
+                  cfg: SolverConfig = SolverConfig(), nmse_fn: Optional[Callable] = None) -> SolverResult:
+    """``S0 [B,R,IJ]``, ``C0 [B,R,K]`` initial factors; ``nll_fn(S, C) -> [B]`` differentiable NLL
+    (sum over maps is what gets back-propagated: maps are independent).  ``nmse_fn(S, C) -> [B]``."""
+    S = S0.detach().clone().requires_grad_(True)
+    Cf = C0.detach().clone().requires_grad_(True)
+    opt_c = torch.optim.Adam([Cf], lr=cfg.lr_c)
+    opt_s = torch.optim.Adam([S], lr=cfg.lr_s)
+    res = SolverResult(S, Cf)
+    if S.is_cuda:
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for it in range(cfg.iters):
+        for _ in range(cfg.c_inner):
+            opt_c.zero_grad(set_to_none=True)
+            cost = nll_fn(S.detach(), Cf).to(torch.float32) + cfg.lam_c * _frob(Cf)
+            cost.sum().backward()
+            opt_c.step()
+        if cfg.project_c:
+            with torch.no_grad():
+                Cf.clamp_(min=0)
+        for _ in range(cfg.s_inner):
+            opt_s.zero_grad(set_to_none=True)
+            cost = nll_fn(S, Cf.detach()).to(torch.float32) + cfg.lam_s * _frob(S)
+            cost.sum().backward()
+            opt_s.step()
+        if cfg.project_s:
+            with torch.no_grad():
+                S.clamp_(min=0)
+        if cfg.track_every and (it % cfg.track_every == 0 or it == cfg.iters - 1):
+            res.cost.append(cost.detach())
+            if nmse_fn is not None:
+                with torch.no_grad():
+                    res.nmse.append(nmse_fn(S, Cf))
+    if S.is_cuda:
+        torch.cuda.synchronize()
+    res.seconds = time.perf_counter() - t0
+    res.iterations = cfg.iters
+    res.S, res.C = S.detach(), Cf.detach()
+    return res
+
+
+def cuda_nll_fn(obs, lik):
+    """The product backend: fused CUDA likelihood of a batch of maps."""
+    from .fused import qmc_nll_batched
+    return lambda S, C: qmc_nll_batched(S, C, obs, lik)
+
+
+def cuda_nmse_fn(T_true: torch.Tensor, offset=None):
+    """NMSE of S*C^T against ``T_true [B,K,IJ]`` without materialising the reconstruction."""
+    from .quantization_model import nmse_factors
+
+    def fn(S, C):
+        return nmse_factors(S, C, T_true, offset=offset).reshape(-1)
+    return fn
+
+
+# ---- synthetic configurations of BASELINE.json ---------------------------------------------------
+CONFIGS = {
+    # one-bit, linear domain (quantization_model.py semantics: +-1e5 sentinels)
+    "cfg1": dict(I=51, J=51, K=64, R=4, f=0.10, levels=2, log_domain=False),
+    # 3-bit / 8 levels (9 boundaries), log domain (quantization_model_log.py semantics)
+    "cfg2": dict(I=101, J=101, K=128, R=8, f=0.20, levels=8, log_domain=True),
+}
+
+
+def synth_problem(name: str, B: int, device, seed: int = 0):
+    """Synthetic instance(s) of a BASELINE config: maps, observations, likelihood, start point."""
+    from . import synth
+    from .fused import make_likelihood, make_obs
+    from .quantization_model import assign_levels
+    c = CONFIGS[name]
+    I, J, K, R = c["I"], c["J"], c["K"], c["R"]
+    maps = synth.generate_maps(B, I, J, K, R, seed=seed, device=device)
+    T = maps.tensor()
+    gen = torch.Generator(device=device).manual_seed(seed + 1)
+    if c["log_domain"]:
+        offset = float(T.median()) * 0.1 + 1e-12
+        X = torch.log(T + offset)
+        bb = synth.equal_mass_boundaries(X, c["levels"])
+        sigma = float((bb[1:] - bb[:-1]).min()) * 2.0
+    else:
+        offset = None
+        X = T
+        if c["levels"] == 2:
+            thr = float(T.median())
+            bb = torch.tensor([0.0, thr, 1.0])
+            sigma = thr
+        else:
+            bb = synth.equal_mass_boundaries(X, c["levels"])
+            sigma = float((bb[1:] - bb[:-1]).min()) * 2.0
+    noisy = X + sigma * torch.randn(X.shape, device=device, generator=gen)
+    Y = assign_levels(noisy, bb)
+    Wx = torch.bernoulli(torch.full(T.shape, c["f"], device=device), generator=gen)
+    lik = make_likelihood(bb, sigma, offset=offset)
+    obs = make_obs(Y, Wx, K, device, B=B, R=R)
+    return dict(maps=maps, T=T, Y=Y, Wx=Wx, bb=bb, sigma=sigma, offset=offset, lik=lik, obs=obs, cfg=c)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="cfg1", choices=sorted(CONFIGS))
+    ap.add_argument("--maps", type=int, default=1)
+    ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args(argv)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pb = synth_problem(args.config, args.maps, dev, args.seed)
+    maps = pb["maps"]
+    cfg = SolverConfig(iters=args.iters, lam_c=1.0, lam_s=1.0, track_every=max(1, args.iters // 10))
+    res = solve_lowrank(0.7 * maps.S_true, 0.9 * maps.C_true, cuda_nll_fn(pb["obs"], pb["lik"]), cfg,
+                        cuda_nmse_fn(pb["T"]))
+    for i, (c, n) in enumerate(zip(res.cost, res.nmse)):
+        print(f"track {i}: cost[0]={c[0].item():.4f} nmse[0]={n.reshape(-1)[0].item():.5f}")
+    print(f"{res.iterations} iterations x {args.maps} maps in {res.seconds:.3f} s -> "
+          f"{res.iterations / res.seconds:.1f} solver iterations/s, "
+          f"{res.iterations * 2 * pb['obs'].nobs / res.seconds:.3e} observed entries/s")
+
+
+if __name__ == "__main__":
+    main()

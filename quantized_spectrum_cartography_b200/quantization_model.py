@@ -173,7 +173,10 @@ def nmse_factors(S, C_, T_target, offset=None):
     materialising the reconstruction (one fused pass; solver loops call this every iteration,
     qmc.ipynb c1:160,215)."""
     R, K = C_.shape[-2:]
-    S3 = _to_dev(S).to(torch.float32).reshape(-1, R, S.shape[-2] * S.shape[-1]).contiguous()
+    if C_.dim() == 3:                        # batched: S [B,R,IJ], C [B,R,K], T_target [B,K,IJ]
+        S3 = _to_dev(S).to(torch.float32).reshape(C_.shape[0], R, -1).contiguous()
+    else:                                    # reference shapes: S [R,1,I,J] or [R,I,J], C [R,K]
+        S3 = _to_dev(S).to(torch.float32).reshape(1, R, -1).contiguous()
     B, _, IJ = S3.shape
     C3 = _to_dev(C_).to(torch.float32).reshape(B, R, K).contiguous()
     Xr = _to_dev(T_target).to(torch.float32).reshape(B, K, IJ).contiguous()

@@ -358,3 +358,76 @@ def test_errors_are_loud(q):
         q.nll_fwd_bwd(S, C, obs, q.make_likelihood(bb, sigma))                     # CPU tensors: no CPU path
     with pytest.raises(_lib.QmcError, match="noise_std"):
         q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, q.make_likelihood(bb, 0.0))
+
+
+def test_solver_trajectory_matches_reference_run(q, nll_golden, fixture_instance):
+    """End to end: 25 alternating Adam iterations of the MLE loop on the shipped
+    instance.  The golden trace was produced by the same loop driven by the reference's own functions
+    on CPU (tests/golden/make_golden.py section 6); cost and NMSE must agree along the whole way."""
+    from quantized_spectrum_cartography_b200 import qmc
+    g = load_golden("solver.npz")
+    case = str(g["case"])
+    c = nll_case_inputs(nll_golden, fixture_instance, f"{case}__p07")
+    S_true = fixture_instance["S_true"]
+    C_true = fixture_instance["C_true"]
+    T_true = oc.get_tensor(S_true.unsqueeze(1), C_true)
+    obs = q.make_obs(c["Y"], c["Wx"], 64, "cuda")
+    lik = q.make_likelihood(c["bb"], c["sigma"])
+    cfg = qmc.SolverConfig(iters=int(g["iters"]), lr_c=float(g["lrC"]), lr_s=float(g["lrS"]), lam_c=float(g["lam"]),
+                           lam_s=float(g["lam"]), track_every=1)
+    S0 = (float(g["s_scale"]) * S_true).reshape(1, 2, -1).cuda()
+    C0 = (float(g["c_scale"]) * C_true).reshape(1, 2, 64).cuda()
+    res = qmc.solve_lowrank(S0, C0, qmc.cuda_nll_fn(obs, lik), cfg, qmc.cuda_nmse_fn(T_true.reshape(1, 64, -1).cuda()))
+    cost = np.array([x.item() for x in res.cost])
+    nmse = np.array([x.item() for x in res.nmse])
+    np.testing.assert_allclose(cost, g["trace"][:, 0], rtol=1e-5)
+    np.testing.assert_allclose(nmse, g["trace"][:, 1], rtol=1e-4, atol=1e-4)     # north star: NMSE within 1e-4
+    assert rel_err(res.C[0].cpu().numpy(), g["C_final"]) < 1e-4
+    assert rel_err(res.S[0].cpu().numpy().reshape(2, 51, 51), g["S_final"]) < 1e-4
+
+
+def test_deep_prior_step_matches_oracle_loop(q):
+    """cfg5 contract on a small batch: generator forward in PyTorch, fused likelihood as the loss;
+    three C/Z iterations agree with the same loop driven by the oracle (seeded random-init
+    Generator256 in eval mode: the trained weights are not shipped with the reference)."""
+    from quantized_spectrum_cartography_b200 import dip
+    B, R, K, I, J = 2, 2, 8, 51, 51
+    torch.manual_seed(0)
+    gen = dip.Generator256().eval()
+    Z0 = torch.randn(B, R, 256)
+    C0 = torch.rand(B, R, K) * 0.2 + 0.05
+    with torch.no_grad():
+        S_true = gen(torch.randn(B * R, 256)).reshape(B, R, -1)
+    T = torch.einsum("brp,brk->bkp", S_true, C0)
+    bb = torch.tensor([0.0, T.median().item(), 10.0])
+    sigma = 0.25 * T.median().item()
+    Y = oc.assign_levels(T + sigma * torch.randn(T.shape), bb)
+    Wx = torch.bernoulli(torch.full(T.shape, 0.2))
+    cfg = dip.DipConfig(iters=3, lam_c=1.0, lam_s=0.1, search_at=-1)
+
+    def oracle_nll(S, C):
+        return torch.stack([oc.masked_nll(S[b].reshape(R, 1, I, J), C[b], Y[b].reshape(K, 1, I, J),
+                                          Wx[b].reshape(K, 1, I, J), bb, sigma, vectorised=True) for b in range(B)])
+
+    ref = dip.solve_deep_prior(gen, Z0, C0, oracle_nll, cfg)
+    gen_d = dip.Generator256().eval()
+    gen_d.load_state_dict(gen.state_dict())
+    gen_d.cuda()
+    obs = q.make_obs(Y.cuda(), Wx.cuda(), K, "cuda", B=B, R=R, tiled=False)
+    lik = q.make_likelihood(bb, sigma)
+    from quantized_spectrum_cartography_b200 import qmc
+    got = dip.solve_deep_prior(gen_d, Z0.cuda(), C0.cuda(), qmc.cuda_nll_fn(obs, lik), cfg)
+    assert rel_err(got["C"].cpu().numpy(), ref["C"].numpy()) < 1e-4
+    # Z's gradient runs through the generator (cuDNN on the GPU, MKL-DNN on the CPU) and the first Adam
+    # steps divide by |g|: latent entries whose gradient is ~0 move by +-lr on fp32 noise.  Compare the
+    # steps taken, in absolute terms (3 steps of lr = 0.01).
+    assert (got["Z"].cpu() - ref["Z"]).abs().max().item() < 2e-3
+    assert rel_err(got["Z"].cpu().numpy(), ref["Z"].numpy()) < 3e-3
+    assert rel_err(got["S"].cpu().numpy(), ref["S"].numpy()) < 3e-3
+    # the latent search only ever lowers the per-map NLL
+    Zs = Z0.clone().cuda()
+    nll_fn = qmc.cuda_nll_fn(obs, lik)
+    with torch.no_grad():
+        before = nll_fn(gen_d(Zs.reshape(B * R, 256)).reshape(B, R, -1), C0.cuda())
+    _, best = dip.latent_search(gen_d, Zs, C0.cuda(), nll_fn, dip.DipConfig(search_draws=5, search_refine=5))
+    assert torch.all(best <= before + 1e-9)
