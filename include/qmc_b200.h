@@ -170,6 +170,23 @@ QMC_API int qmc_nll_fwd_bwd_gather_host(const float* S_host, const float* C_host
                                 float* gC_scratch_dev, double* nll_host, float* gS_host,
                                 float* gC_host, void* stream);
 
+/* ---- dense-sampling path: tcgen05 tensor cores, likelihood as the GEMM epilogue ------------------ */
+
+/* code8[b][p][k] = (Wx[b][k][p] != 0) ? Y[b][k][p] : 255 -- one byte per dense entry, pixel-major, the
+ * observation format of the dense kernel (levels 0..254).  wx_dev may be NULL (everything observed). */
+QMC_API int qmc_dense_pack(const void* y_dev, int y_is_int64, const float* wx_dev, int B, int K, int IJ,
+                   uint8_t* code_out_dev, void* stream);
+
+/* Same contract as qmc_nll_fwd_bwd_gather for ONE instance (B = 1) with S [R][IJ], C [R][K] contiguous:
+ * X = S*C^T, gS = G*C and gC = G^T*S are formed by tcgen05.mma (kind::tf32, 3xTF32 operand split, fp32
+ * accumulators in tensor memory); X and G = dNLL/dX never touch HBM.  Supported: K a multiple of 32 and
+ * <= 256, R <= 16, levels <= 255; otherwise QMC_ERR_UNSUPPORTED (use the gather entry point). */
+QMC_API int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, const uint8_t* code_dev,
+                          const qmc_likelihood_t* lik, int IJ, int K, int R, double* nll_out_dev,
+                          float* gS_out_dev, float* gC_out_dev, void* stream);
+/* Shared-memory bytes of the dense kernel for a geometry (0 = unsupported). */
+QMC_API int64_t qmc_dense_smem_bytes(int K, int R);
+
 /* ---- a1/a2/a10 helpers kept importable by the reference's call surface ------------------------ */
 
 /* X[b][k][p] = sum_r S[b][r][p]*C[b][r][k] (+ optional log link): get_tensor, quantization_model.py:79-86 */

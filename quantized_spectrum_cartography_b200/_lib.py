@@ -1,7 +1,7 @@
 """ctypes binding of libqmc_b200.so (C ABI: include/qmc_b200.h).
 
 There is no fallback: if the shared object is missing or a symbol is absent, importing this
-module raises.  Build with ``python -m quantized_spectrum_cartography_b200.build``.
+module raises.  Build with ``python quantized_spectrum_cartography_b200/build.py``.
 """
 from __future__ import annotations
 
@@ -48,6 +48,9 @@ SIGNATURES = {
     "qmc_tiled_smem_bytes": (_L, [_I, _I, _I, _I]),
     "qmc_nll_fwd_bwd_gather_host": (_I, [_P, _P, _P, _P, C.POINTER(ObsView), C.POINTER(Likelihood),
                                          _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "qmc_dense_pack": (_I, [_P, _I, _P, _I, _I, _I, _P, _P]),
+    "qmc_nll_fwd_bwd_dense": (_I, [_P, _P, _P, C.POINTER(Likelihood), _I, _I, _I, _P, _P, _P, _P]),
+    "qmc_dense_smem_bytes": (_L, [_I, _I]),
     "qmc_get_tensor": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "qmc_nmse_terms": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
 }
@@ -57,7 +60,7 @@ def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build the CUDA library first "
-            "(python -m quantized_spectrum_cartography_b200.build).  There is no CPU fallback.")
+            "(python quantized_spectrum_cartography_b200/build.py).  There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported

@@ -1,7 +1,8 @@
 """Build libqmc_b200.so in-tree with nvcc for sm_100a.
 
-    python -m quantized_spectrum_cartography_b200.build        # rebuild if sources are newer
-    python -m quantized_spectrum_cartography_b200.build -f     # force
+    python quantized_spectrum_cartography_b200/build.py        # rebuild if sources are newer
+    python quantized_spectrum_cartography_b200/build.py -f     # force
+(run it as a script: importing the package needs the library to exist already)
 
 The library is a plain CUDA shared object (C ABI, include/qmc_b200.h); it does not link against
 torch.  The .so is git-ignored but travels to the GPU box with the repo snapshot.

@@ -1,0 +1,516 @@
+// Dense-sampling path (cfg4: one large instance, ~50 % of the entries observed): the reconstruction
+// X = S*C^T and both gradient contractions run on the 5th-generation tensor cores (tcgen05, fp32
+// accumulators in tensor memory), with the quantized likelihood as the epilogue between them, so
+// neither X nor g = dNLL/dX ever exists in HBM.  Replaces the same reference idiom as the gather
+// kernels (qmc/quantization_model.py:22-39,57-61,70-86; qmc/qmc.ipynb c1:145-153).
+//
+// Per CTA (256 threads, persistent over 128-pixel tiles):
+//   MMA1  D1[128 px x K bands]  = S_tile * C^T          kind::tf32, 3xTF32 split (hi*hi + hi*lo + lo*hi)
+//   epilogue (8 warps): tcgen05.ld a 32-column slab of D1 per thread, read the 1-byte codes of the
+//         same entries, evaluate log P and g, store g (hi/lo TF32 parts) into shared memory twice:
+//         G[128 px x 32 bands] with bands contiguous and G^T[32 bands x 128 px] with pixels contiguous,
+//         both as K-major UMMA operands (MN-major TF32 operands in the no-swizzle layout read as zeros
+//         on this part, measured; hence the explicit transposed copy)
+//   MMA2  D2[128 px x 16]      += G * C                 (gS tile)
+//   MMA3  D3[32(64) bands x 16] += G^T * S_tile          (gC block; M = 64 instruction, rows 32..63 unused)
+// D2 is written to gS after the last band block of a tile, D3 accumulates over all tiles of the CTA
+// and is added to gC once at the end.
+//
+// Observation format: one byte per dense entry, pixel-major code8[IJ][K], 255 = not observed
+// (qmc_dense_pack builds it from the reference's Y / Wx).
+#include "qmc_common.cuh"
+
+namespace qmc {
+
+constexpr int DT_PIX = 128;    // pixels per tile = TMEM lanes
+constexpr int DT_BLK = 32;     // bands per G block
+constexpr int DT_RP = 16;      // padded rank of the gradient MMAs (N)
+constexpr int DT_THREADS = 256;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_D2 = 256, COL_D3 = 272;
+
+struct DenseParams {
+  const float* S;        // [R][IJ]
+  const float* C;        // [R][K]
+  const uint8_t* code;   // [IJ][K]
+  double* nll;
+  float* gS;             // [R][IJ]
+  float* gC;             // [R][K]
+  int IJ, K, R, Rp8, n_tiles;
+  int n_bounds;
+  float inv_a, offset, thr;
+  float bounds[QMC_MAX_BOUNDS];
+};
+
+enum : int { DEPI_STABLE = 0, DEPI_REFERENCE = 1, DEPI_ONEBIT = 2 };
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // shared-memory matrix descriptor, no swizzle (interleaved 8x16-byte core matrices), sm_100 version 1
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N, bool a_mn_major) {
+  return (1u << 4) /*D = f32*/ | (2u << 7) /*A = tf32*/ | (2u << 10) /*B = tf32*/ |
+         ((a_mn_major ? 1u : 0u) << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void dmbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void dmbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "DW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DD_%=;\n\t"
+      "bra DW_%=;\n\t"
+      "DD_%=:\n\t}" ::"r"(s_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// TF32 split: hi keeps the 10 explicit mantissa bits the tensor core reads, lo is the exact rest
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+template <int EPI, bool LOGD>
+__device__ __forceinline__ BinEval dense_eval(const DenseParams& prm, float t, int lvl, float& dxdt) {
+  float x = t;
+  dxdt = 1.0f;
+  if (LOGD) {
+    const float u = t + prm.offset;
+    x = logf(u);
+    dxdt = 1.0f / u;
+  }
+  if (EPI == DEPI_ONEBIT) return probit_one_sided_fast(prm.thr, lvl ? -prm.inv_a : prm.inv_a, x);
+  if (EPI == DEPI_REFERENCE) return probit_bin_reference(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
+  return probit_bin_stable<true>(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
+}
+
+// Shared memory map (bytes).  All operand regions are 128-byte aligned.
+//   A1  : S tile split, K-major [chunk j][pixel][16 B], chunks = 3*Rp8/4          128*16*chunks
+//   B1  : C split,      K-major [chunk j][band ][16 B]                             K*16*chunks
+//   B2h/B2l : C as [chunk of 4 bands][r-group][r%8][16 B]  (N = 16, K-major)       K/4*256 each
+//   B3h/B3l : S tile as [chunk of 4 pixels][r-group][r%8][16 B]                    32*256 each
+//   Gh/Gl   : g block  [chunk of 4 bands][pixel][16 B]                             8*2048 each
+//   GTh/GTl : g block transposed [chunk of 4 pixels][band][16 B], chunk pitch 528 B (32 rows + 16 B of
+//             padding so that the scalar stores of 32 consecutive pixels hit 32 different banks), plus
+//             512 B of slack because the M = 64 instruction reads 64 rows per chunk
+constexpr uint32_t GT_PITCH = 528;
+struct DenseSmem {
+  uint32_t a1, b1, b2h, b2l, b3h, b3l, gh, gl, gth, gtl, total;
+};
+__host__ __device__ inline DenseSmem dense_smem_map(int K, int Rp8) {
+  const uint32_t chunks = 3 * Rp8 / 4;
+  DenseSmem m;
+  uint32_t o = 0;
+  m.a1 = o; o += DT_PIX * 16 * chunks;
+  m.b1 = o; o += (uint32_t)K * 16 * chunks;
+  m.b2h = o; o += (uint32_t)(K / 4) * 256;
+  m.b2l = o; o += (uint32_t)(K / 4) * 256;
+  m.b3h = o; o += 32 * 256;
+  m.b3l = o; o += 32 * 256;
+  m.gh = o; o += 8 * 2048;
+  m.gl = o; o += 8 * 2048;
+  m.gth = o; o += 32 * GT_PITCH + 512;
+  m.gtl = o; o += 32 * GT_PITCH + 512;
+  m.total = o;
+  return m;
+}
+
+template <int EPI, bool LOGD, bool GRAD>
+__global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams prm) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  __shared__ uint64_t bar1, bar2;
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ double wsum[DT_THREADS / 32];
+
+  const int K = prm.K, R = prm.R, Rp8 = prm.Rp8;
+  const int chunks1 = 3 * Rp8 / 4;
+  const DenseSmem map = dense_smem_map(K, Rp8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant, 16-band half of a 32-band block
+  const int row = quad * 32 + lane;              // pixel row of this thread inside the tile
+  const uint32_t sbase = s_u32(dsm);
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_sh)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    dmbar_init(&bar1, 1);
+    dmbar_init(&bar2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // B1 (C split for MMA1) and B2h/B2l (C for MMA2): built once, C is the same for every tile
+  for (int k = tid; k < K; k += DT_THREADS) {
+    float ch[16], cl[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float c = (r < R) ? __ldg(prm.C + (size_t)r * K + k) : 0.0f;
+      ch[r] = tf32_hi(c);
+      cl[r] = c - ch[r];
+    }
+    // B1 row = band k, elements [Ch(0..Rp8) | Cl | Ch]
+    for (int j = 0; j < chunks1; ++j) {
+      const int e = 4 * j, seg = e / Rp8, r0 = e % Rp8;
+      const float* src = (seg == 1) ? cl : ch;
+      *reinterpret_cast<float4*>(dsm + map.b1 + (size_t)j * K * 16 + k * 16) = make_float4(src[r0], src[r0 + 1], src[r0 + 2], src[r0 + 3]);
+    }
+    // B2: element (n = r, kk = band k) at chunk k/4, group r/8, row r%8, word k%4
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const uint32_t o = (k >> 2) * 256 + (r >> 3) * 128 + (r & 7) * 16 + (k & 3) * 4;
+      *reinterpret_cast<float*>(dsm + map.b2h + o) = ch[r];
+      *reinterpret_cast<float*>(dsm + map.b2l + o) = cl[r];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_sh;
+  const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+
+  const uint32_t idesc1 = umma_idesc_tf32(128, K, false);
+  const uint32_t idesc2 = umma_idesc_tf32(128, DT_RP, false);
+  const uint32_t idesc3 = umma_idesc_tf32(64, DT_RP, false);
+
+  float nll_part = 0.0f;
+  uint32_t ph1 = 0, ph2 = 0;
+  bool d3_started = false;   // D3 blocks accumulate over all tiles of this CTA
+  const int nblk = K / DT_BLK;
+
+  for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+    const int p0 = tile * DT_PIX;
+    // ---- stage the S tile: A1 (MMA1) and B3h/B3l (MMA3) -------------------------------------------
+    {
+      const int p = tid & 127, rh = tid >> 7;   // pixel, rank half (8 ranks each)
+      const bool inside = p0 + p < prm.IJ;
+      float sh[8], sl[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rh * 8 + i;
+        const float s = (inside && r < R) ? __ldg(prm.S + (size_t)r * prm.IJ + p0 + p) : 0.0f;
+        sh[i] = tf32_hi(s);
+        sl[i] = s - sh[i];
+        const uint32_t o = (p >> 2) * 256 + (r >> 3) * 128 + (r & 7) * 16 + (p & 3) * 4;
+        if (GRAD) {
+          *reinterpret_cast<float*>(dsm + map.b3h + o) = sh[i];
+          *reinterpret_cast<float*>(dsm + map.b3l + o) = sl[i];
+        }
+      }
+      // A1 row = pixel p, elements [Sh | Sh | Sl]; this thread owns ranks rh*8 .. rh*8+7 (if < Rp8)
+      if (rh * 8 < Rp8) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int jr = rh * 2 + q;   // chunk index inside one Rp8-wide segment
+          const float4 h4 = make_float4(sh[4 * q], sh[4 * q + 1], sh[4 * q + 2], sh[4 * q + 3]);
+          const float4 l4 = make_float4(sl[4 * q], sl[4 * q + 1], sl[4 * q + 2], sl[4 * q + 3]);
+          const int per = Rp8 / 4;
+          *reinterpret_cast<float4*>(dsm + map.a1 + (size_t)(jr) * 2048 + p * 16) = h4;
+          *reinterpret_cast<float4*>(dsm + map.a1 + (size_t)(per + jr) * 2048 + p * 16) = h4;
+          *reinterpret_cast<float4*>(dsm + map.a1 + (size_t)(2 * per + jr) * 2048 + p * 16) = l4;
+        }
+      }
+    }
+    fence_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- MMA1: D1 = [Sh|Sh|Sl] * [Ch|Cl|Ch]^T ------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      const int ksteps = 3 * Rp8 / 8;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t ad = umma_desc(sbase + map.a1 + ks * 2 * 2048, 2048, 128);
+        const uint64_t bd = umma_desc(sbase + map.b1 + ks * 2 * K * 16, K * 16, 128);
+        umma_tf32(tmem, ad, bd, idesc1, ks > 0);
+      }
+      umma_commit(&bar1);
+    }
+    dmbar_wait(&bar1, ph1);
+    ph1 ^= 1;
+    tc_fence_after();
+
+    // ---- epilogue, one 64-band block at a time ------------------------------------------------------
+    const bool inside = p0 + row < prm.IJ;
+    const uint8_t* crow = prm.code + (size_t)(p0 + row) * K;
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int k0 = blk * DT_BLK + half * 16;   // first band of this thread's 16-column slab
+      float x[16];
+      tmem_ld16(tlane + (uint32_t)k0, x);
+      uint32_t cw[4];
+      if (inside) {
+        const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(crow + k0));
+        cw[0] = c0.x; cw[1] = c0.y; cw[2] = c0.z; cw[3] = c0.w;
+      } else {
+        cw[0] = cw[1] = cw[2] = cw[3] = 0xffffffffu;
+      }
+      // likelihood of the slab: x[] is overwritten by g = dNLL/dt (0 where nothing was observed)
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int code = (cw[c4] >> (8 * i)) & 0xff;
+          float g = 0.0f;
+          if (code != 255) {
+            float dxdt;
+            const BinEval ev = dense_eval<EPI, LOGD>(prm, x[4 * c4 + i], code, dxdt);
+            nll_part -= ev.logp;
+            g = ev.gx * dxdt;
+          }
+          x[4 * c4 + i] = g;
+        }
+      }
+      if (GRAD) {
+        if (blk > 0) {
+          // the previous block's gradient MMAs must have consumed the G buffers before they are overwritten
+          dmbar_wait(&bar2, ph2);
+          ph2 ^= 1;
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 h4 = make_float4(tf32_hi(x[4 * c4]), tf32_hi(x[4 * c4 + 1]), tf32_hi(x[4 * c4 + 2]), tf32_hi(x[4 * c4 + 3]));
+          const float4 l4 = make_float4(x[4 * c4] - h4.x, x[4 * c4 + 1] - h4.y, x[4 * c4 + 2] - h4.z, x[4 * c4 + 3] - h4.w);
+          const uint32_t o = (uint32_t)(half * 4 + c4) * 2048 + row * 16;
+          *reinterpret_cast<float4*>(dsm + map.gh + o) = h4;
+          *reinterpret_cast<float4*>(dsm + map.gl + o) = l4;
+          // transposed copy: element (band, pixel) at chunk pixel/4, row band, word pixel%4
+          const uint32_t ot = (uint32_t)(row >> 2) * GT_PITCH + (uint32_t)(half * 16 + 4 * c4) * 16 + (row & 3) * 4;
+          *reinterpret_cast<float*>(dsm + map.gth + ot) = h4.x;
+          *reinterpret_cast<float*>(dsm + map.gth + ot + 16) = h4.y;
+          *reinterpret_cast<float*>(dsm + map.gth + ot + 32) = h4.z;
+          *reinterpret_cast<float*>(dsm + map.gth + ot + 48) = h4.w;
+          *reinterpret_cast<float*>(dsm + map.gtl + ot) = l4.x;
+          *reinterpret_cast<float*>(dsm + map.gtl + ot + 16) = l4.y;
+          *reinterpret_cast<float*>(dsm + map.gtl + ot + 32) = l4.z;
+          *reinterpret_cast<float*>(dsm + map.gtl + ot + 48) = l4.w;
+        }
+        fence_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          // MMA2: D2[128 x 16] += G_blk * C_blk   (K = 32 bands of this block, 4 steps of 8)
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t ga = (term == 2) ? map.gl : map.gh;
+            const uint32_t cb = (term == 1) ? map.b2l : map.b2h;
+            for (int ks = 0; ks < DT_BLK / 8; ++ks) {
+              const uint64_t ad = umma_desc(sbase + ga + ks * 2 * 2048, 2048, 128);
+              const uint64_t bd = umma_desc(sbase + cb + (blk * (DT_BLK / 4) + ks * 2) * 256, 256, 128);
+              umma_tf32(tmem + COL_D2, ad, bd, idesc2, (blk | term | ks) != 0);
+            }
+          }
+          // MMA3: D3_blk[bands x 16] += G_blk^T * S_tile   (K = 128 pixels, 16 steps of 8; M = 64
+          // instruction whose rows 32..63 read the following chunk and are never looked at)
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t ga = (term == 2) ? map.gtl : map.gth;
+            const uint32_t sb = (term == 1) ? map.b3l : map.b3h;
+            for (int ks = 0; ks < DT_PIX / 8; ++ks) {
+              const uint64_t ad = umma_desc(sbase + ga + ks * 2 * GT_PITCH, GT_PITCH, 128);
+              const uint64_t bd = umma_desc(sbase + sb + ks * 2 * 256, 256, 128);
+              umma_tf32(tmem + COL_D3 + blk * DT_RP, ad, bd, idesc3, d3_started || (term | ks) != 0);
+            }
+          }
+          umma_commit(&bar2);
+        }
+      }
+    }
+    d3_started = true;
+    if (GRAD) {
+      // ---- gS tile out of D2 ---------------------------------------------------------------------
+      dmbar_wait(&bar2, ph2);
+      ph2 ^= 1;
+      tc_fence_after();
+      if (half == 0) {
+        float v[16];
+        tmem_ld16(tlane + COL_D2, v);
+        if (inside) {
+#pragma unroll
+          for (int r = 0; r < 16; ++r)
+            if (r < R) prm.gS[(size_t)r * prm.IJ + p0 + row] = v[r];
+        }
+      }
+    }
+    // all TMEM reads of this tile are done before the next tile's MMAs overwrite D1 / D2
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // ---- gC out of D3, NLL -----------------------------------------------------------------------------
+  if (GRAD && blockIdx.x < prm.n_tiles) {
+    tc_fence_after();
+    if (half == 0 && quad < 2) {
+      for (int blk = 0; blk < nblk; ++blk) {
+        float v[16];
+        // warp-wide load; M = 64 accumulator: rows 0..15 in lanes 0..15 of quadrant 0, rows 16..31 in
+        // lanes 0..15 of quadrant 1 (rows 32..63, quadrants 2 and 3, are the unused half)
+        tmem_ld16(tlane + COL_D3 + blk * DT_RP, v);
+        const int band = blk * DT_BLK + quad * 16 + lane;
+        if (lane < 16) {
+#pragma unroll
+          for (int r = 0; r < 16; ++r)
+            if (r < R) atomicAdd(prm.gC + (size_t)r * K + band, v[r]);
+        }
+      }
+    }
+  }
+  double w = warp_sum((double)nll_part);
+  if (lane == 0) wsum[warp] = w;
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < DT_THREADS / 32; ++i) tot += wsum[i];
+    if (tot != 0.0) atomicAdd(prm.nll, tot);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+  }
+}
+
+// code8[b][p][k] = Wx != 0 ? Y : 255, from the reference's band-major [K][IJ] arrays
+template <typename YT>
+__global__ void dense_pack_kernel(const YT* __restrict__ y, const float* __restrict__ wx, int K, int IJ,
+                                  uint8_t* __restrict__ code) {
+  __shared__ uint8_t t[32][33];
+  const int p0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const size_t plane = (size_t)blockIdx.z * K * IJ;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, p = p0 + threadIdx.x;
+    uint8_t c = 255;
+    if (k < K && p < IJ) {
+      const size_t o = plane + (size_t)k * IJ + p;
+      if (!wx || wx[o] != 0.0f) c = (uint8_t)y[o];
+    }
+    t[i][threadIdx.x] = c;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, k = k0 + threadIdx.x;
+    if (p < IJ && k < K) code[plane + (size_t)p * K + k] = t[threadIdx.x][i];
+  }
+}
+
+template <int EPI>
+static int dense_launch(const DenseParams& prm, bool logd, bool grad, int grid, size_t smem, cudaStream_t st) {
+#define QMC_DENSE_GO(L, G)                                                                                   \
+  do {                                                                                                       \
+    auto kern = dense_kernel<EPI, L, G>;                                                                     \
+    QMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    kern<<<grid, DT_THREADS, smem, st>>>(prm);                                                               \
+  } while (0)
+  if (logd) { if (grad) QMC_DENSE_GO(true, true); else QMC_DENSE_GO(true, false); }
+  else { if (grad) QMC_DENSE_GO(false, true); else QMC_DENSE_GO(false, false); }
+#undef QMC_DENSE_GO
+  count_launch();
+  QMC_CUDA_CHECK(cudaGetLastError());
+  return QMC_OK;
+}
+
+}  // namespace qmc
+
+using namespace qmc;
+
+extern "C" int qmc_dense_pack(const void* y_dev, int y_is_int64, const float* wx_dev, int B, int K, int IJ,
+                              uint8_t* code_out_dev, void* stream) {
+  QMC_REQUIRE(y_dev && code_out_dev, "null argument");
+  QMC_REQUIRE(B > 0 && K > 0 && IJ > 0 && B <= 65535 && (K + 31) / 32 <= 65535, "bad sizes");
+  dim3 grid((IJ + 31) / 32, (K + 31) / 32, B), block(32, 8);
+  if (y_is_int64)
+    dense_pack_kernel<int64_t><<<grid, block, 0, (cudaStream_t)stream>>>((const int64_t*)y_dev, wx_dev, K, IJ, code_out_dev);
+  else
+    dense_pack_kernel<uint8_t><<<grid, block, 0, (cudaStream_t)stream>>>((const uint8_t*)y_dev, wx_dev, K, IJ, code_out_dev);
+  count_launch();
+  QMC_CUDA_CHECK(cudaGetLastError());
+  return QMC_OK;
+}
+
+extern "C" int64_t qmc_dense_smem_bytes(int K, int R) {
+  if (K <= 0 || K > 256 || (K % DT_BLK) != 0 || R <= 0 || R > DT_RP) return 0;
+  return (int64_t)dense_smem_map(K, R <= 8 ? 8 : 16).total;
+}
+
+extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, const uint8_t* code_dev,
+                                     const qmc_likelihood_t* lik, int IJ, int K, int R, double* nll_out_dev,
+                                     float* gS_out_dev, float* gC_out_dev, void* stream) {
+  QMC_REQUIRE(S_dev && C_dev && code_dev && lik && nll_out_dev, "null argument");
+  QMC_REQUIRE(IJ > 0 && R > 0, "bad sizes");
+  if (K <= 0 || K > 256 || (K % DT_BLK) != 0)
+    return set_error(QMC_ERR_UNSUPPORTED, "dense path needs K a multiple of %d and <= 256 (got %d)", DT_BLK, K);
+  if (R > DT_RP) return set_error(QMC_ERR_UNSUPPORTED, "dense path needs rank <= %d (got %d)", DT_RP, R);
+  QMC_REQUIRE(lik->n_bounds >= 2 && lik->n_bounds <= QMC_MAX_BOUNDS - 1, "n_bounds %d out of range (255 is the 'unobserved' code)", lik->n_bounds);
+  QMC_REQUIRE(lik->noise_std > 0.0f, "noise_std must be positive");
+  const bool grad = !(lik->flags & QMC_FORWARD_ONLY);
+  QMC_REQUIRE(!grad || (gS_out_dev && gC_out_dev), "gradient outputs are NULL without QMC_FORWARD_ONLY");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  DenseParams prm;
+  prm.S = S_dev; prm.C = C_dev; prm.code = code_dev; prm.nll = nll_out_dev; prm.gS = gS_out_dev; prm.gC = gC_out_dev;
+  prm.IJ = IJ; prm.K = K; prm.R = R; prm.Rp8 = R <= 8 ? 8 : 16;
+  prm.n_tiles = (IJ + DT_PIX - 1) / DT_PIX;
+  prm.n_bounds = lik->n_bounds;
+  prm.inv_a = 1.0f / probit_scale(lik->noise_std);
+  prm.offset = lik->offset;
+  for (int i = 0; i < lik->n_bounds; ++i) prm.bounds[i] = lik->bounds[i];
+  prm.thr = lik->n_bounds >= 3 ? lik->bounds[1] : 0.0f;
+  int epi = DEPI_STABLE;
+  if (lik->flags & QMC_EPI_REFERENCE) epi = DEPI_REFERENCE;
+  else if (lik->n_bounds == 3) {
+    const float lo = lik->bounds[0], hi = lik->bounds[2];
+    if (lo <= -1e4f && hi >= 1e4f && (-lo * 0.5f) * prm.inv_a > 30.0f && (hi * 0.5f) * prm.inv_a > 30.0f) epi = DEPI_ONEBIT;
+  }
+  const bool logd = (lik->flags & QMC_LOG_DOMAIN) != 0;
+
+  QMC_CUDA_CHECK(cudaMemsetAsync(nll_out_dev, 0, sizeof(double), st));
+  if (grad) QMC_CUDA_CHECK(cudaMemsetAsync(gC_out_dev, 0, sizeof(float) * (size_t)R * K, st));
+  const size_t smem = dense_smem_map(K, prm.Rp8).total;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = prm.n_tiles < sms ? prm.n_tiles : sms;
+  switch (epi) {
+    case DEPI_ONEBIT: return dense_launch<DEPI_ONEBIT>(prm, logd, grad, grid, smem, st);
+    case DEPI_REFERENCE: return dense_launch<DEPI_REFERENCE>(prm, logd, grad, grid, smem, st);
+    default: return dense_launch<DEPI_STABLE>(prm, logd, grad, grid, smem, st);
+  }
+}

@@ -19,13 +19,14 @@ def declared_symbols():
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for must in ("qmc_quantize_levels", "qmc_obs_count_scan", "qmc_obs_fill", "qmc_nll_fwd_bwd_gather",
-                 "qmc_nll_fwd_bwd_gather_host", "qmc_abi_version", "qmc_last_error"):
+                 "qmc_nll_fwd_bwd_gather_host", "qmc_nll_fwd_bwd_dense", "qmc_dense_pack", "qmc_abi_version",
+                 "qmc_last_error"):
         assert must in syms, must
 
 
 def test_library_loads_and_exports_every_declared_symbol():
-    from quantized_spectrum_cartography_b200 import build as qbuild
-    path = qbuild.build()
+    import __graft_entry__
+    path = __graft_entry__._load_builder().build()
     lib = ctypes.CDLL(path)
     for sym in declared_symbols():
         assert hasattr(lib, sym), f"{sym} declared in include/qmc_b200.h but not exported by {path}"

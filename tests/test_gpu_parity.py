@@ -431,3 +431,49 @@ def test_deep_prior_step_matches_oracle_loop(q):
         before = nll_fn(gen_d(Zs.reshape(B * R, 256)).reshape(B, R, -1), C0.cuda())
     _, best = dip.latent_search(gen_d, Zs, C0.cuda(), nll_fn, dip.DipConfig(search_draws=5, search_refine=5))
     assert torch.all(best <= before + 1e-9)
+
+
+@pytest.mark.parametrize("IJ,K,R,levels,log_domain,f", [(300, 64, 4, 2, False, 0.5), (1000, 128, 16, 8, False, 0.5),
+                                                       (515, 256, 16, 8, True, 0.5), (128, 96, 9, 4, False, 0.9),
+                                                       (4096, 256, 16, 2, False, 0.3)])
+def test_dense_tcgen05_path_vs_oracle_and_gather(q, IJ, K, R, levels, log_domain, f):
+    """The tensor-core path (X = S*C^T, gS = G*C, gC = G^T*S on tcgen05 with 3xTF32 operands, the
+    likelihood as the epilogue) against the float64 oracle and against the gather kernel."""
+    from quantized_spectrum_cartography_b200 import _lib, dense
+    assert dense.dense_supported(K, R)
+    S, C, Y, Wx, bb, sigma, off = _random_instance(1, IJ, 1, K, R, f, levels, seed=IJ + K, log_domain=log_domain)
+    lik = q.make_likelihood(bb, sigma, offset=off)
+    dobs = dense.pack_dense(Y[0].cuda(), Wx[0].cuda(), K)
+    assert dobs.nobs == int(Wx.sum().item())
+    code = dobs.code.cpu().numpy()
+    want_code = np.where(Wx[0].numpy().T != 0, Y[0].numpy().T, 255)
+    np.testing.assert_array_equal(code, want_code)
+    before = _lib.launch_count()
+    nll, gS, gC = dense.nll_fwd_bwd_dense(S[0].cuda(), C[0].cuda(), dobs, lik)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == before + 1
+    want = oc.nll_and_grads_fp64(S[0].reshape(R, 1, IJ, 1), C[0], Y[0].reshape(K, 1, IJ, 1), Wx[0].reshape(K, 1, IJ, 1),
+                                 bb, sigma, offset=off, sentinels=off is None)
+    assert nll.item() == pytest.approx(want[0], rel=NLL_RTOL)
+    assert rel_err(gS.cpu().numpy(), want[1].reshape(R, -1)) < GRAD_RTOL
+    assert rel_err(gC.cpu().numpy(), want[2]) < GRAD_RTOL
+    # and the gather kernel on the same instance
+    obs = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, 1)
+    nll_g, gS_g, gC_g = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik, algo=_lib.QMC_ALGO_FLAT)
+    # (X differs in the last bits between the two paths -- 3xTF32 products vs fp32 FMAs -- and g is
+    #  steep in x, so the two CUDA paths agree with each other no better than with the oracle)
+    assert nll.item() == pytest.approx(nll_g[0].item(), rel=2e-6)
+    assert rel_err(gS.cpu().numpy(), gS_g[0].cpu().numpy()) < GRAD_RTOL
+    assert rel_err(gC.cpu().numpy(), gC_g[0].cpu().numpy()) < GRAD_RTOL
+    # forward only
+    nll_f, _, _ = dense.nll_fwd_bwd_dense(S[0].cuda(), C[0].cuda(), dobs, lik, want_grad=False)
+    assert nll_f.item() == pytest.approx(nll.item(), rel=1e-12)
+
+
+def test_dense_path_rejects_what_it_cannot_run(q):
+    from quantized_spectrum_cartography_b200 import _lib, dense
+    assert not dense.dense_supported(100, 4) and not dense.dense_supported(512, 4) and not dense.dense_supported(64, 17)
+    S, C, Y, Wx, bb, sigma, off = _random_instance(1, 64, 1, 80, 2, 0.5, 2, seed=3)
+    dobs = dense.pack_dense(Y[0].cuda(), Wx[0].cuda(), 80)
+    with pytest.raises(_lib.QmcError, match="multiple of 32"):
+        dense.nll_fwd_bwd_dense(S[0].cuda(), C[0].cuda(), dobs, q.make_likelihood(bb, sigma))
