@@ -55,7 +55,12 @@ def _world() -> tuple[int, int]:
 # batched independent maps: no collective
 # -------------------------------------------------------------------------------------------------
 def _cuda_local_eval(S3, C3, obs, lik, want_grad=True):
+    """Product evaluator: the gather kernels for an ObsSet, the tcgen05 kernel for a DenseObs."""
+    from .dense import DenseObs, nll_fwd_bwd_dense
     from .fused import nll_fwd_bwd
+    if isinstance(obs, DenseObs):
+        nll, gS, gC = nll_fwd_bwd_dense(S3[0], C3[0], obs, lik, want_grad=want_grad)
+        return nll.reshape(1), None if gS is None else gS.unsqueeze(0), None if gC is None else gC.unsqueeze(0)
     return nll_fwd_bwd(S3, C3, obs, lik, want_grad=want_grad)
 
 
@@ -124,9 +129,11 @@ class ShardedInstance:
 
     @classmethod
     def from_dense(cls, Y, Wx, K: int, R: int, lik, *, mode: str = "flat", device=None, align: int = 1,
-                   build: Optional[Callable] = None, local_eval: Callable = _cuda_local_eval) -> "ShardedInstance":
+                   dense: Optional[bool] = None, build: Optional[Callable] = None,
+                   local_eval: Callable = _cuda_local_eval) -> "ShardedInstance":
         """``Y``/``Wx``: the full instance ``[K, IJ]`` (reference layout ``[K,1,I,J]`` accepted); each
-        rank keeps only its pixel block."""
+        rank keeps only its pixel block.  ``dense``: use the tcgen05 dense kernel for the local block
+        (default: when the geometry is supported and at least a quarter of the entries are observed)."""
         if mode not in ("flat", "pixel_block"):
             raise ValueError(mode)
         rank, world = _world()
@@ -136,8 +143,11 @@ class ShardedInstance:
         Yl = Yk[:, lo:hi].contiguous()
         Wl = None if Wx is None else Wx.reshape(K, -1)[:, lo:hi].contiguous()
         if build is None:
+            from .dense import dense_supported, pack_dense
             from .fused import make_obs
-            obs = make_obs(Yl, Wl, K, device, B=1, R=R, tiled=False)
+            if dense is None:
+                dense = dense_supported(K, R) and Wl is not None and float(Wl.float().mean()) >= 0.25
+            obs = pack_dense(Yl, Wl, K) if dense else make_obs(Yl, Wl, K, device, B=1, R=R, tiled=False)
         else:
             obs = build(Yl, Wl)
         return cls(IJ, K, R, lo, hi, obs, lik, mode, local_eval, align)

@@ -109,6 +109,6 @@ def equal_mass_boundaries(samples: torch.Tensor, levels: int) -> torch.Tensor:
     last = max of the samples: the goal of qmc/utils.py:57-74 (`_find_boundaries`), via quantiles."""
     x = samples.reshape(-1).float()
     if x.numel() > 4_000_000:
-        x = x[torch.randperm(x.numel(), device=x.device)[:4_000_000]]
+        x = x[:: x.numel() // 4_000_000]          # deterministic subsample (every rank must get the same table)
     qs = torch.linspace(0, 1, levels + 1, device=x.device)
     return torch.quantile(x, qs).cpu()
