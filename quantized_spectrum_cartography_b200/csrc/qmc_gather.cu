@@ -8,6 +8,8 @@
 //           memory; every warp owns a pixel sub-tile exclusively, so gS updates are plain
 //           shared-memory read-modify-writes (no atomics); entries arrive sorted by band inside a
 //           sub-tile, so gC accumulates in registers and is reduced across the warp once per band.
+#include <cstdlib>
+
 #include "qmc_common.cuh"
 
 namespace qmc {
@@ -499,6 +501,13 @@ static int launch_one(const GatherParams& prm, int algo, cudaStream_t st) {
     constexpr int UNR = RP <= 4 ? 2 : 1;
     auto kern = gc_private(prm.K, RP, prm.tile_warps) ? gather_tiled_kernel<RP, EPI, LOGD, GRAD, UNR, true>
                                                        : gather_tiled_kernel<RP, EPI, LOGD, GRAD, UNR, false>;
+    if (RP == 4 && EPI == EPI_ONEBIT && GRAD && !LOGD && gc_private(prm.K, RP, prm.tile_warps)) {
+      // deeper interleave for few-warp tiles (long rows, low occupancy): 4 chunks in flight per warp
+      const char* e = getenv("QMC_TILED_UNR");
+      const int want = e ? atoi(e) : (prm.tile_warps <= 4 ? 4 : 2);
+      if (want == 4) kern = gather_tiled_kernel<RP, EPI, LOGD, GRAD, (RP == 4 ? 4 : UNR), true>;
+      if (want == 1) kern = gather_tiled_kernel<RP, EPI, LOGD, GRAD, (RP == 4 ? 1 : UNR), true>;
+    }
     QMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ctas = (int64_t)prm.B * prm.tiles_per_map;
     QMC_REQUIRE(ctas <= 0x7fffffff, "too many CTAs (%lld)", (long long)ctas);

@@ -41,6 +41,9 @@ class SolverConfig:
     project_c: bool = True      # c1:156-157
     project_s: bool = True
     track_every: int = 1        # the notebook evaluates NMSE every iteration (a host sync each time)
+    cuda_graph: bool = False    # capture one alternating iteration (2 evaluations, 2 Adam steps, the
+                                # projections) in a CUDA graph and replay it: removes the ~20 host-side
+                                # launches per iteration that bound small batches
 
 
 @dataclass
@@ -64,31 +67,75 @@ def solve_lowrank(S0: torch.Tensor, C0: torch.Tensor, nll_fn: Callable[[torch.Te
     (sum over maps is what gets back-propagated: maps are independent).  ``nmse_fn(S, C) -> [B]``."""
     S = S0.detach().clone().requires_grad_(True)
     Cf = C0.detach().clone().requires_grad_(True)
-    opt_c = torch.optim.Adam([Cf], lr=cfg.lr_c)
-    opt_s = torch.optim.Adam([S], lr=cfg.lr_s)
+    capturable = bool(cfg.cuda_graph)
+    opt_c = torch.optim.Adam([Cf], lr=cfg.lr_c, capturable=capturable)
+    opt_s = torch.optim.Adam([S], lr=cfg.lr_s, capturable=capturable)
     res = SolverResult(S, Cf)
     if S.is_cuda:
         torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for it in range(cfg.iters):
+    def c_step():
+        opt_c.zero_grad(set_to_none=False)
+        cost = nll_fn(S.detach(), Cf).to(torch.float32) + cfg.lam_c * _frob(Cf)
+        cost.sum().backward()
+        opt_c.step()
+        return cost
+
+    def s_step():
+        opt_s.zero_grad(set_to_none=False)
+        cost = nll_fn(S, Cf.detach()).to(torch.float32) + cfg.lam_s * _frob(S)
+        cost.sum().backward()
+        opt_s.step()
+        return cost
+
+    def iteration():
         for _ in range(cfg.c_inner):
-            opt_c.zero_grad(set_to_none=True)
-            cost = nll_fn(S.detach(), Cf).to(torch.float32) + cfg.lam_c * _frob(Cf)
-            cost.sum().backward()
-            opt_c.step()
+            c_step()
         if cfg.project_c:
             with torch.no_grad():
                 Cf.clamp_(min=0)
+        cost = None
         for _ in range(cfg.s_inner):
-            opt_s.zero_grad(set_to_none=True)
-            cost = nll_fn(S, Cf.detach()).to(torch.float32) + cfg.lam_s * _frob(S)
-            cost.sum().backward()
-            opt_s.step()
+            cost = s_step()
         if cfg.project_s:
             with torch.no_grad():
                 S.clamp_(min=0)
+        return cost
+
+    graph = None
+    if cfg.cuda_graph:
+        if not S.is_cuda:
+            raise ValueError("cuda_graph needs CUDA tensors")
+        # warm up on a side stream (allocator, Adam state, kernel attributes), restore, then capture
+        S_keep, C_keep = S.detach().clone(), Cf.detach().clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                iteration()
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.no_grad():
+            S.copy_(S_keep)
+            Cf.copy_(C_keep)
+        for opt in (opt_c, opt_s):              # reset the moments the warm-up touched
+            for st in opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_cost = iteration()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+
+    for it in range(cfg.iters):
+        if graph is not None:
+            graph.replay()
+            cost = static_cost
+        else:
+            cost = iteration()
         if cfg.track_every and (it % cfg.track_every == 0 or it == cfg.iters - 1):
-            res.cost.append(cost.detach())
+            res.cost.append(cost.detach().clone())
             if nmse_fn is not None:
                 with torch.no_grad():
                     res.nmse.append(nmse_fn(S, Cf))
@@ -163,11 +210,12 @@ def main(argv=None):
     ap.add_argument("--maps", type=int, default=1)
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--graph", action="store_true", help="replay one captured iteration (CUDA graph)")
     args = ap.parse_args(argv)
     dev = torch.device("cuda", torch.cuda.current_device())
     pb = synth_problem(args.config, args.maps, dev, args.seed)
     maps = pb["maps"]
-    cfg = SolverConfig(iters=args.iters, lam_c=1.0, lam_s=1.0, track_every=max(1, args.iters // 10))
+    cfg = SolverConfig(iters=args.iters, lam_c=1.0, lam_s=1.0, track_every=max(1, args.iters // 10), cuda_graph=args.graph)
     res = solve_lowrank(0.7 * maps.S_true, 0.9 * maps.C_true, cuda_nll_fn(pb["obs"], pb["lik"]), cfg,
                         cuda_nmse_fn(pb["T"]))
     for i, (c, n) in enumerate(zip(res.cost, res.nmse)):

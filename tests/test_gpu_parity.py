@@ -487,3 +487,25 @@ def test_dense_path_rejects_what_it_cannot_run(q):
     dobs = dense.pack_dense(Y[0].cuda(), Wx[0].cuda(), 80)
     with pytest.raises(_lib.QmcError, match="multiple of 32"):
         dense.nll_fwd_bwd_dense(S[0].cuda(), C[0].cuda(), dobs, q.make_likelihood(bb, sigma))
+
+
+def test_cuda_graph_solver_matches_eager(q):
+    """One captured alternating iteration replayed N times == N eager iterations (batched maps, tiled
+    kernel: no atomics, so the two runs see identical arithmetic)."""
+    from quantized_spectrum_cartography_b200 import qmc
+    B, I, J, K, R = 6, 20, 21, 16, 4
+    S, C, Y, Wx, bb, sigma, off = _random_instance(B, I, J, K, R, 0.3, 2, seed=77)
+    lik = q.make_likelihood(bb, sigma)
+    obs = q.make_obs(Y.cuda(), Wx.cuda(), K, "cuda", B=B, R=R, tiled=True, tile_warps=4)
+    T = torch.einsum("brp,brk->bkp", S, C).cuda()
+    out = []
+    for graph in (False, True):
+        cfg = qmc.SolverConfig(iters=12, lam_c=1.0, lam_s=1.0, track_every=4, cuda_graph=graph)
+        out.append(qmc.solve_lowrank(0.8 * S.cuda(), 1.1 * C.cuda(), qmc.cuda_nll_fn(obs, lik), cfg, qmc.cuda_nmse_fn(T)))
+    a, b = out
+    assert rel_err(b.S.cpu().numpy(), a.S.cpu().numpy()) < 1e-5
+    assert rel_err(b.C.cpu().numpy(), a.C.cpu().numpy()) < 1e-5
+    for ca, cb in zip(a.cost, b.cost):
+        np.testing.assert_allclose(cb.cpu().numpy(), ca.cpu().numpy(), rtol=1e-5)
+    for na, nb in zip(a.nmse, b.nmse):
+        np.testing.assert_allclose(nb.cpu().numpy(), na.cpu().numpy(), rtol=1e-4)
