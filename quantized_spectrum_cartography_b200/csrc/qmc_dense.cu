@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
   const uint32_t idesc2 = umma_idesc_tf32(128, DT_RP, false);
   const uint32_t idesc3 = umma_idesc_tf32(64, DT_RP, false);
 
-  float nll_part = 0.0f;
+  float nll_part = 0.0f;   // per tile (<= 256 terms) in fp32, folded into nll_acc in fp64 after every tile
+  double nll_acc = 0.0;
   uint32_t ph1 = 0, ph2 = 0;
   bool d3_started = false;   // D3 blocks accumulate over all tiles of this CTA
   const int nblk = K / DT_BLK;
@@ -371,6 +372,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
         }
       }
     }
+    nll_acc += (double)nll_part;
+    nll_part = 0.0f;
     // all TMEM reads of this tile are done before the next tile's MMAs overwrite D1 / D2
     tc_fence_before();
     __syncthreads();
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
       }
     }
   }
-  double w = warp_sum((double)nll_part);
+  double w = warp_sum(nll_acc);
   if (lane == 0) wsum[warp] = w;
   tc_fence_before();
   __syncthreads();
