@@ -25,7 +25,8 @@ namespace qmc {
 constexpr int DT_PIX = 128;    // pixels per tile = TMEM lanes
 constexpr int DT_BLK = 32;     // bands per G block
 constexpr int DT_RP = 16;      // padded rank of the gradient MMAs (N)
-constexpr int DT_THREADS = 256;
+constexpr int DT_THREADS = 512;   // 16 warps: 4 per TMEM lane quadrant, each takes an 8-band slab of a block
+constexpr int DT_SLAB = DT_BLK / (DT_THREADS / 128);
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_D2 = 256, COL_D3 = 272;
 
@@ -109,6 +110,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // TF32 split: hi keeps the 10 explicit mantissa bits the tensor core reads, lo is the exact rest
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
   const int chunks1 = 3 * Rp8 / 4;
   const DenseSmem map = dense_smem_map(K, Rp8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant, 16-band half of a 32-band block
+  const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant, which 8-band slab of a 32-band block
   const int row = quad * 32 + lane;              // pixel row of this thread inside the tile
   const uint32_t sbase = s_u32(dsm);
 
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
     const int p0 = tile * DT_PIX;
     // ---- stage the S tile: A1 (MMA1) and B3h/B3l (MMA3) -------------------------------------------
-    {
+    if (tid < 256) {
       const int p = tid & 127, rh = tid >> 7;   // pixel, rank half (8 ranks each)
       const bool inside = p0 + p < prm.IJ;
       float sh[8], sl[8];
@@ -276,19 +287,19 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
     const bool inside = p0 + row < prm.IJ;
     const uint8_t* crow = prm.code + (size_t)(p0 + row) * K;
     for (int blk = 0; blk < nblk; ++blk) {
-      const int k0 = blk * DT_BLK + half * 16;   // first band of this thread's 16-column slab
-      float x[16];
-      tmem_ld16(tlane + (uint32_t)k0, x);
-      uint32_t cw[4];
+      const int k0 = blk * DT_BLK + half * DT_SLAB;   // first band of this thread's 8-column slab
+      float x[DT_SLAB];
+      tmem_ld8(tlane + (uint32_t)k0, x);
+      uint32_t cw[DT_SLAB / 4];
       if (inside) {
-        const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(crow + k0));
-        cw[0] = c0.x; cw[1] = c0.y; cw[2] = c0.z; cw[3] = c0.w;
+        const uint2 c0 = __ldg(reinterpret_cast<const uint2*>(crow + k0));
+        cw[0] = c0.x; cw[1] = c0.y;
       } else {
-        cw[0] = cw[1] = cw[2] = cw[3] = 0xffffffffu;
+        cw[0] = cw[1] = 0xffffffffu;
       }
       // likelihood of the slab: x[] is overwritten by g = dNLL/dt (0 where nothing was observed)
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
+      for (int c4 = 0; c4 < DT_SLAB / 4; ++c4) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int code = (cw[c4] >> (8 * i)) & 0xff;
@@ -309,14 +320,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
           ph2 ^= 1;
         }
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
+        for (int c4 = 0; c4 < DT_SLAB / 4; ++c4) {
           const float4 h4 = make_float4(tf32_hi(x[4 * c4]), tf32_hi(x[4 * c4 + 1]), tf32_hi(x[4 * c4 + 2]), tf32_hi(x[4 * c4 + 3]));
           const float4 l4 = make_float4(x[4 * c4] - h4.x, x[4 * c4 + 1] - h4.y, x[4 * c4 + 2] - h4.z, x[4 * c4 + 3] - h4.w);
-          const uint32_t o = (uint32_t)(half * 4 + c4) * 2048 + row * 16;
+          const uint32_t o = (uint32_t)(half * (DT_SLAB / 4) + c4) * 2048 + row * 16;
           *reinterpret_cast<float4*>(dsm + map.gh + o) = h4;
           *reinterpret_cast<float4*>(dsm + map.gl + o) = l4;
           // transposed copy: element (band, pixel) at chunk pixel/4, row band, word pixel%4
-          const uint32_t ot = (uint32_t)(row >> 2) * GT_PITCH + (uint32_t)(half * 16 + 4 * c4) * 16 + (row & 3) * 4;
+          const uint32_t ot = (uint32_t)(row >> 2) * GT_PITCH + (uint32_t)(half * DT_SLAB + 4 * c4) * 16 + (row & 3) * 4;
           *reinterpret_cast<float*>(dsm + map.gth + ot) = h4.x;
           *reinterpret_cast<float*>(dsm + map.gth + ot + 16) = h4.y;
           *reinterpret_cast<float*>(dsm + map.gth + ot + 32) = h4.z;
