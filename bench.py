@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-solver", action="store_true")
     ap.add_argument("--tile-warps", type=int, default=8)
     ap.add_argument("--smem-budget-kb", type=int, default=100)
+    ap.add_argument("--obs-layout", default="lanes", choices=["lanes", "rows"],
+                    help="lanes: per-lane band walks, conflict-free steps (default); rows: band rows per sub-tile")
     ap.add_argument("--bank-mod", type=int, default=-1, help="-1: conflict-free order for the rank; 0: pixel order")
     ap.add_argument("--layout", default="pixel_major", choices=["pixel_major", "emitter_major"],
                     help="device storage of S for the kernel-only number")
@@ -109,7 +111,8 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # workload
 # -------------------------------------------------------------------------------------------------
-def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_budget_kb: int = 100, bank_mod: int = -1):
+def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_budget_kb: int = 100, bank_mod: int = -1,
+                   lanes: bool = True):
     """cfg3 on one GPU: synthetic maps, one-bit observations, tiled compact observation set.
     Seeds: `seed` data, `seed+1` noise and mask."""
     import torch
@@ -139,9 +142,9 @@ def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_bud
                                   torch.cuda.current_stream().cuda_stream))
     del noisy
     Wx = torch.bernoulli(torch.full(T.shape, c["sampling"], device=device), generator=gen)
-    n_sub, sub, tw = q.plan_tiles(IJ, K, R, tile_warps, smem_budget_kb * 1024)
+    n_sub, sub, tw = q.plan_tiles(IJ, K, R, tile_warps, smem_budget_kb * 1024, lanes=lanes)
     obs = q.build_obs(Y, Wx, K, IJ, n_maps, n_sub=n_sub, sub_pixels=sub, tile_warps=tw,
-                      bank_mod=bank_mod if bank_mod >= 0 else q.bank_mod_for_rank(R))
+                      bank_mod=0 if lanes else (bank_mod if bank_mod >= 0 else q.bank_mod_for_rank(R)), lanes=lanes)
     lik = q.make_likelihood(bb, sigma)
     S_eval = (0.8 * maps.S_true).contiguous()                            # evaluation point
     C_eval = maps.C_true.contiguous()
@@ -248,7 +251,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     from quantized_spectrum_cartography_b200._lib import check, lib
 
     wl = build_workload(args.maps, dev, seed=2 * rank, tile_warps=args.tile_warps, smem_budget_kb=args.smem_budget_kb,
-                        bank_mod=args.bank_mod)
+                        bank_mod=args.bank_mod, lanes=args.obs_layout == "lanes")
     obs, lik, R, K, IJ = wl["obs"], wl["lik"], wl["R"], wl["K"], wl["IJ"]
     B = args.maps
     S = wl["S"]
@@ -263,7 +266,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     def step():
         check(lib.qmc_nll_fwd_bwd_gather(S.data_ptr(), S.stride(0), S.stride(1), S.stride(2), Cf.data_ptr(),
-                                         C.byref(view), C.byref(lik), B, IJ, K, R, _lib.QMC_ALGO_TILED,
+                                         C.byref(view), C.byref(lik), B, IJ, K, R, _lib.QMC_ALGO_AUTO,
                                          obs.tile_warps, nll.data_ptr(), gS.data_ptr(), gC.data_ptr(),
                                          stream.cuda_stream))
 
@@ -315,7 +318,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         def e2e_step():
             check(lib.qmc_nll_fwd_bwd_gather_host(
                 Sh.data_ptr(), Ch.data_ptr(), Sd.data_ptr(), Cd.data_ptr(), C.byref(view), C.byref(lik), B, IJ, K, R,
-                _lib.QMC_ALGO_TILED, obs.tile_warps, nll.data_ptr(), gSd.data_ptr(), gCd.data_ptr(), nllh.data_ptr(),
+                _lib.QMC_ALGO_AUTO, obs.tile_warps, nll.data_ptr(), gSd.data_ptr(), gCd.data_ptr(), nllh.data_ptr(),
                 gSh.data_ptr(), gCh.data_ptr(), stream.cuda_stream))
 
         for _ in range(max(3, min(args.warmup, 5))):
@@ -370,7 +373,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "gather_tiled_kernel<4,ONEBIT>",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "gather_lanes_kernel<4,ONEBIT>" if obs.lanes else "gather_tiled_kernel<4,ONEBIT>",
                 "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_launch_ms,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
@@ -391,7 +394,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": c["workload"], "maps_per_gpu": B, "shape": "51x51x64", "rank": R,
                    "sampling": c["sampling"], "levels": c["levels"], "observed_entries_per_gpu": obs.nobs,
-                   "S_layout": args.layout, "tile_warps": obs.tile_warps, "tiles_per_map": obs.n_sub // obs.tile_warps, "l2": "inputs %.2f GB/step per GPU > 126 MB L2 (no flush needed)" % (alg_bytes / 1e9),
+                   "S_layout": args.layout, "tile_warps": obs.tile_warps, "tiles_per_map": obs.n_sub // obs.tile_warps,
+                   "obs_layout": "lanes" if obs.lanes else "rows", "obs_padding": round(obs.padding_fraction(), 4), "l2": "inputs %.2f GB/step per GPU > 126 MB L2 (no flush needed)" % (alg_bytes / 1e9),
                    "evaluation_point": "0.8*S_true, C_true", "threshold": wl["thr"], "sigma": wl["sigma"]},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "solver": solver,
         "evaluations_per_s": args.steps / (total_ms * 1e-3) * world,

@@ -37,7 +37,7 @@ extern "C" {
 #define QMC_API
 #endif
 
-#define QMC_ABI_VERSION 1
+#define QMC_ABI_VERSION 2
 #define QMC_MAX_BOUNDS 257 /* uint8 levels: at most 256 levels = 257 boundaries (qmc/utils.py:24) */
 #define QMC_MAX_RANK 32
 
@@ -87,6 +87,14 @@ typedef struct qmc_obs_view {
   const int64_t* row_off_dev;
   int32_t n_sub;       /* pixel sub-tiles per map */
   int32_t sub_pixels;  /* pixels per sub-tile */
+  /* Lane-stream layout (qmc_obs_build_lanes), NULL otherwise: the entries of every (map, sub-tile)
+   * stream re-cut so that each lane of the owning warp walks one band at a time and the 32 entries
+   * of a step hit 32 different pixels.  word = level << 24 | band << 15 | tile-local pixel; level
+   * 0xFF marks padding.  Steps are stored in groups of four, lane-interleaved: word(t, lane) at
+   * stream_off[s] + ((t / 4) * 32 + lane) * 4 + t % 4.  idx/lvl/row_off are not used by the kernel. */
+  const uint32_t* words_dev;
+  const int64_t* stream_off_dev; /* B*n_sub + 1 word offsets, multiples of 128 */
+  const int32_t* nrows_dev;      /* B*n_sub steps per stream, multiples of 4 */
 } qmc_obs_view_t;
 
 QMC_API int qmc_abi_version(void);
@@ -125,6 +133,19 @@ QMC_API int qmc_obs_fill(const void* y_dev, int y_is_int64, const float* wx_dev,
                  int n_sub, int sub_pixels, int bank_mod, const int64_t* row_off_dev,
                  int32_t* idx_out_dev, uint8_t* lvl_out_dev, void* stream);
 
+/* Re-cut a row-ordered observation set (n_sub, sub_pixels as built by qmc_obs_count_scan/qmc_obs_fill
+ * with bank_mod = 0) into the lane-stream layout for tiles of tile_warps sub-tiles.  idx_rows/lvl_rows
+ * are used as scratch and come back permuted inside their rows.  stream_off_dev: caller-chosen
+ * capacities in words (multiples of 128; 32 * (1.3 * n * ceil(K/32) / K + 8) words for a stream of n
+ * entries is ample); nrows_out_dev receives the steps actually used; *overflow_dev is set to 1 if a
+ * stream did not fit its capacity.  K <= 256, levels <= 254, tile_warps * sub_pixels + 32 <= 32768. */
+QMC_API int qmc_obs_build_lanes(int32_t* idx_rows_dev, uint8_t* lvl_rows_dev, const int64_t* row_off_dev,
+                        int B, int K, int IJ, int n_sub, int sub_pixels, int tile_warps,
+                        const int64_t* stream_off_dev, uint32_t* words_out_dev, int32_t* nrows_out_dev,
+                        int32_t* overflow_dev, void* stream);
+/* Shared-memory bytes of the lanes kernel for a geometry (0 if it cannot run it). */
+QMC_API int64_t qmc_lanes_smem_bytes(int K, int R, int sub_pixels, int tile_warps);
+
 /* ---- a2..a7: fused masked low-rank reconstruction + quantized NLL + factor gradients ---------- */
 
 /* algorithms of qmc_nll_fwd_bwd_gather */
@@ -132,8 +153,10 @@ enum {
   QMC_ALGO_AUTO = 0,
   QMC_ALGO_FLAT = 1,  /* one thread per observed entry, factors gathered through L2, gradients by
                          warp-aggregated global atomics: single small/medium instance */
-  QMC_ALGO_TILED = 2  /* one CTA per (map, pixel tile): factor rows staged in shared memory, band
+  QMC_ALGO_TILED = 2, /* one CTA per (map, pixel tile): factor rows staged in shared memory, band
                          segments reduced in registers, no global atomics on gS: batched maps */
+  QMC_ALGO_LANES = 3  /* as TILED, on a lane-stream observation set: each lane keeps its band's C row and gC
+                         accumulator in registers; gS rows are plain shared-memory updates */
 };
 
 /*

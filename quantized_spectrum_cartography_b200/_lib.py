@@ -16,7 +16,7 @@ QMC_MAX_RANK = 32
 QMC_LOG_DOMAIN = 1 << 0
 QMC_EPI_REFERENCE = 1 << 1
 QMC_FORWARD_ONLY = 1 << 2
-QMC_ALGO_AUTO, QMC_ALGO_FLAT, QMC_ALGO_TILED = 0, 1, 2
+QMC_ALGO_AUTO, QMC_ALGO_FLAT, QMC_ALGO_TILED, QMC_ALGO_LANES = 0, 1, 2, 3
 
 
 class Likelihood(C.Structure):
@@ -28,7 +28,8 @@ class Likelihood(C.Structure):
 class ObsView(C.Structure):
     """qmc_obs_view_t"""
     _fields_ = [("idx_dev", C.c_void_p), ("lvl_dev", C.c_void_p), ("row_off_dev", C.c_void_p),
-                ("n_sub", C.c_int32), ("sub_pixels", C.c_int32)]
+                ("n_sub", C.c_int32), ("sub_pixels", C.c_int32),
+                ("words_dev", C.c_void_p), ("stream_off_dev", C.c_void_p), ("nrows_dev", C.c_void_p)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -43,6 +44,8 @@ SIGNATURES = {
     "qmc_obs_scan_ws_elems": (_L, [_L]),
     "qmc_obs_count_scan": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "qmc_obs_fill": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "qmc_obs_build_lanes": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "qmc_lanes_smem_bytes": (_L, [_I, _I, _I, _I]),
     "qmc_nll_fwd_bwd_gather": (_I, [_P, _L, _L, _L, _P, C.POINTER(ObsView), C.POINTER(Likelihood),
                                     _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "qmc_tiled_smem_bytes": (_L, [_I, _I, _I, _I]),

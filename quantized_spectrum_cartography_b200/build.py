@@ -16,7 +16,22 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libqmc_b200.so")
-SOURCES = ["qmc_abi.cu", "qmc_quantize.cu", "qmc_gather.cu", "qmc_dense.cu"]
+# (source, object stem, extra flags, headers it depends on besides the common ones)
+FAMILIES = {1: "flat", 2: "tiled", 3: "lanes"}
+RANKS = (1, 2, 4, 8, 16, 32)
+COMMON_DEPS = ["qmc_common.cuh", "erfcx_coeffs.h", os.path.join("..", "..", "include", "qmc_b200.h")]
+
+
+def units() -> list[tuple[str, str, list[str], list[str]]]:
+    u = [("qmc_abi.cu", "qmc_abi", [], []), ("qmc_quantize.cu", "qmc_quantize", [], []),
+         ("qmc_dense.cu", "qmc_dense", [], []), ("qmc_gather.cu", "qmc_gather", [], ["qmc_gather_common.cuh"])]
+    for fam, name in FAMILIES.items():
+        for rp in RANKS:
+            u.append(("qmc_gather_inst.cu", f"qmc_gather_{name}_r{rp}", [f"-DQMC_FAMILY={fam}", f"-DQMC_RP={rp}"],
+                      ["qmc_gather_common.cuh", f"qmc_gather_{name}.cuh"]))
+    return u
+
+
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -31,44 +46,70 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def sources() -> list[str]:
-    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+def _obj(stem: str) -> str:
+    return os.path.join(PKG, "build", stem + ".o")
+
+
+def _stale(stem: str, src: str, deps: list[str]) -> bool:
+    obj = _obj(stem)
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    files = [os.path.join(CSRC, src)] + [os.path.join(CSRC, d) for d in COMMON_DEPS + deps]
+    return any(os.path.getmtime(f) > t for f in files)
 
 
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(os.path.dirname(PKG), "include", "qmc_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(_stale(stem, src, deps) or os.path.getmtime(_obj(stem)) > t for src, stem, _, deps in units())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -> str:
+    """Compile the stale translation units (``jobs`` at a time, default: all cores) and link."""
     if not force and not needs_build():
         return LIB
-    objs = []
-    procs = []
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
-    for src in sources():
-        obj = os.path.join(PKG, "build", os.path.basename(src)[:-3] + ".o")
-        objs.append(obj)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    log = []
-    for src, p in procs:
-        out, _ = p.communicate()
-        log.append(out)
-        if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    todo = [(src, stem, fl) for src, stem, fl, deps in units() if force or _stale(stem, src, deps)]
+    jobs = jobs or int(os.environ.get("QMC_BUILD_JOBS", os.cpu_count() or 4))
+    running: list[tuple[str, subprocess.Popen]] = []
+    logs = {}
+
+    def reap(block: bool):
+        for item in list(running):
+            stem, p = item
+            if block or p.poll() is not None:
+                out, _ = p.communicate()
+                running.remove(item)
+                logs[stem] = out
+                if p.returncode != 0:
+                    for _, q in running:
+                        q.kill()
+                    raise RuntimeError(f"nvcc failed on {stem}:\n{out}")
+                if block:
+                    return
+
+    for src, stem, fl in todo:
+        while len(running) >= jobs:
+            reap(block=False)
+            if len(running) >= jobs:
+                import time
+                time.sleep(0.2)
+        cmd = [_nvcc(), *NVCC_FLAGS, *fl, "-c", os.path.join(CSRC, src), "-o", _obj(stem)]
+        running.append((stem, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    while running:
+        reap(block=True)
+    objs = [_obj(stem) for _, stem, _, _ in units()]
     link = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    with open(os.path.join(PKG, "build", "ptxas.log"), "w") as f:
-        f.write("\n".join(log))
+    for stem, out in logs.items():
+        with open(os.path.join(PKG, "build", stem + ".ptxas.log"), "w") as f:
+            f.write(out)
     if verbose:
-        print("\n".join(log))
+        print("\n".join(logs.values()))
     return LIB
 
 

@@ -1,0 +1,170 @@
+// Shared pieces of the observed-entry ("gather") kernels: launch parameters, the per-entry likelihood
+// dispatch, TMA bulk copies and shared-memory access helpers.  See qmc_gather.cu for the overview.
+#pragma once
+#include <cstdlib>
+#include <type_traits>
+
+#include "qmc_common.cuh"
+
+namespace qmc {
+
+struct GatherParams {
+  const float* S;
+  int64_t sB, sR, sP;
+  const float* C;
+  const int32_t* idx;
+  const uint8_t* lvl;
+  const int64_t* row_off;
+  const uint32_t* words;      // lane-stream layout (qmc_obs_build_lanes)
+  const int64_t* stream_off;  // lane-stream layout: first word of every (map, sub-tile) stream
+  const int32_t* nrows;       // lane-stream layout: steps per stream (multiple of 4)
+  double* nll;
+  float* gS;
+  float* gC;
+  int n_sub, sub_pixels;
+  int B, IJ, K, R;
+  uint32_t div_magic;  // k = umulhi(idx, div_magic) >> div_shift  (idx < 2^31)
+  int div_shift;
+  int tiles_per_map, tile_warps;
+  float inv_a, offset;
+  float thr;  // one-bit fast path threshold
+  float bounds[QMC_MAX_BOUNDS];
+};
+
+enum : int { EPI_STABLE = 0, EPI_REFERENCE = 1, EPI_ONEBIT = 2 };
+
+__device__ __forceinline__ int fast_div(uint32_t n, uint32_t magic, int shift) {
+  return (int)(__umulhi(n, magic) >> shift);
+}
+
+template <int EPI, bool LOGD>
+__device__ __forceinline__ BinEval eval_entry(const GatherParams& prm, float t, int lvl, float& dxdt) {
+  float x = t;
+  dxdt = 1.0f;
+  if (LOGD) {
+    const float u = t + prm.offset;
+    x = logf(u);
+    dxdt = 1.0f / u;
+  }
+  if (EPI == EPI_ONEBIT) {
+    return probit_one_sided_fast(prm.thr, lvl ? -prm.inv_a : prm.inv_a, x);
+  } else if (EPI == EPI_REFERENCE) {
+    return probit_bin_reference(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
+  } else {
+    return probit_bin_stable<true>(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
+  }
+}
+
+constexpr size_t kPrivateGcBytes = 32 * 1024;
+
+__host__ __device__ inline bool gc_private(int K, int RP, int W) {
+  return (size_t)W * K * RP * sizeof(float) <= kPrivateGcBytes;
+}
+
+static size_t tiled_smem_bytes(int K, int RP, int sub_pixels, int W, bool grad) {
+  const size_t TP = (size_t)sub_pixels * W;
+  const size_t wc = gc_private(K, RP, W) ? W : 1;
+  size_t fl = TP * RP + (size_t)K * RP;
+  if (grad) fl += TP * RP + wc * K * RP;
+  if (grad) fl += (size_t)W * 32 * RP;  // per-lane scratch rows for masked-off updates
+  return fl * sizeof(float) + (size_t)W * (K + 2) * sizeof(int) + 16;
+}
+
+// ---- bulk (TMA) copies of a contiguous tile ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic in the loop) --
+// read-only data of the main loop (S and C tiles): plain asm, free to be scheduled
+__device__ __forceinline__ float4 lds128_ro(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32_ro(uint32_t a) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+// read-modify-write data (gradient tiles): ordered
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ int lds32i(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+
+constexpr uint32_t LW_PIX_MASK = 0x7FFFu;
+constexpr uint32_t LW_BAND_MASK = 0x00FF8000u;
+constexpr int LW_BAND_SHIFT = 15;
+
+static size_t lanes_smem_bytes(int K, int RP, int sub_pixels, int W, bool grad) {
+  const size_t TP = (size_t)sub_pixels * W + 32;
+  size_t fl = TP * RP + (size_t)(K + 1) * RP;
+  if (grad) fl += TP * RP + (size_t)W * (K + 1) * RP;
+  return fl * sizeof(float) + 16;
+}
+// per-family launchers, one explicit instantiation per padded rank (qmc_gather_inst.cu)
+template <int RP> int launch_flat_rp(const GatherParams& prm, int epi, bool logd, bool grad, cudaStream_t st);
+template <int RP> int launch_tiled_rp(const GatherParams& prm, int epi, bool logd, bool grad, cudaStream_t st);
+template <int RP> int launch_lanes_rp(const GatherParams& prm, int epi, bool logd, bool grad, cudaStream_t st);
+
+// expands to the (EPI, LOGD, GRAD) switch around GO(EPI, LOGD, GRAD)
+#define QMC_GATHER_SWITCH(GO)                                                        \
+  do {                                                                               \
+    switch (epi) {                                                                   \
+      case EPI_ONEBIT:                                                               \
+        if (logd) { if (grad) GO(EPI_ONEBIT, true, true); else GO(EPI_ONEBIT, true, false); }          \
+        else { if (grad) GO(EPI_ONEBIT, false, true); else GO(EPI_ONEBIT, false, false); }             \
+        break;                                                                       \
+      case EPI_REFERENCE:                                                            \
+        if (logd) { if (grad) GO(EPI_REFERENCE, true, true); else GO(EPI_REFERENCE, true, false); }    \
+        else { if (grad) GO(EPI_REFERENCE, false, true); else GO(EPI_REFERENCE, false, false); }       \
+        break;                                                                       \
+      default:                                                                       \
+        if (logd) { if (grad) GO(EPI_STABLE, true, true); else GO(EPI_STABLE, true, false); }          \
+        else { if (grad) GO(EPI_STABLE, false, true); else GO(EPI_STABLE, false, false); }             \
+    }                                                                                \
+  } while (0)
+
+}  // namespace qmc

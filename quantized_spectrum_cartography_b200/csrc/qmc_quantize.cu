@@ -145,6 +145,131 @@ __global__ void obs_fill_kernel(const YT* __restrict__ y, const float* __restric
   }
 }
 
+// ---- lane streams -------------------------------------------------------------------------------
+// One warp per (map, sub-tile) stream.  The stream's rows (bands) are dealt to the 32 lanes in snake
+// order of their sizes (largest, ..., 32nd | 64th, ..., 33rd | ...), so every lane owns about the same
+// number of entries, and a lane walks its bands one after the other: in the gather kernel the lane
+// keeps C[band] and the band's gC accumulator in registers.  Step t of the stream takes one entry
+// from every lane; the entries of a step have pairwise distinct pixels (hard: the kernel updates gS
+// rows without atomics) and, where the lane still has a choice, distinct shared-memory bank groups
+// inside each quarter-warp (soft).  A lane that cannot comply, or has nothing left, emits a padding
+// word.  Word = level << 24 | band << 15 | tile-local pixel; padding = 0xFF << 24 | band << 15 |
+// (tile pixels + lane), i.e. a dummy pixel row private to the lane.  Steps are stored in groups of
+// four, lane-interleaved: word(t, lane) at ((t / 4) * 32 + lane) * 4 + t % 4.
+constexpr int LANE_GROUP = 4;
+constexpr uint32_t LANE_PAD_LEVEL = 0xFFu;
+
+template <int G>
+__global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict__ lvl,
+                                 const int64_t* __restrict__ row_off, int64_t n_streams, int K, int IJ, int n_sub,
+                                 int sub_pixels, int tile_warps, const int64_t* __restrict__ stream_off,
+                                 uint32_t* __restrict__ words, int32_t* __restrict__ nrows,
+                                 int32_t* __restrict__ overflow) {
+  extern __shared__ int16_t band_of_rank_all[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (s >= n_streams) return;
+  int16_t* band_of_rank = band_of_rank_all + wib * K;
+  const int64_t row0 = s * K;
+  const int64_t beg = row_off[row0];
+  const int st = (int)(s % n_sub);
+  const int TP = tile_warps * sub_pixels;
+  const int p0 = (st / tile_warps) * TP;  // first pixel of the tile this sub-tile belongs to
+  // rank the bands by size (descending, ties by band index)
+  for (int k = lane; k < K; k += 32) {
+    const int64_t ck = row_off[row0 + k + 1] - row_off[row0 + k];
+    int rank = 0;
+    for (int j = 0; j < K; ++j) {
+      const int64_t cj = row_off[row0 + j + 1] - row_off[row0 + j];
+      rank += (cj > ck) || (cj == ck && j < k);
+    }
+    band_of_rank[rank] = (int16_t)k;
+  }
+  __syncwarp();
+  int bands[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int r = (g & 1) ? 32 * g + 31 - lane : 32 * g + lane;
+    bands[g] = r < K ? band_of_rank[r] : -1;
+  }
+  int g = -1, band = K, cur = 0, end = 0;  // band K: the dummy band of a lane that owns nothing
+  const int64_t out0 = stream_off[s];
+  const int cap = (int)((stream_off[s + 1] - out0) >> 5);
+  const uint32_t pad_pix = (uint32_t)(TP + lane);
+  int step = 0;
+  while (true) {
+    // move on to the lane's next non-empty band
+    while (cur >= end && g < G) {
+      ++g;
+      int nb = -1;
+#pragma unroll
+      for (int gg = 0; gg < G; ++gg)
+        if (gg == g) nb = bands[gg];
+      if (g < G && nb >= 0) {
+        const int c0 = (int)(row_off[row0 + nb] - beg), e0 = (int)(row_off[row0 + nb + 1] - beg);
+        if (e0 > c0) { band = nb; cur = c0; end = e0; }
+      }
+    }
+    const bool has = cur < end;
+    if (!__any_sync(0xffffffffu, has)) break;
+    const int navail = end - cur;
+    bool active = has, won = false;
+    int tries = 0, q = cur;
+    int id = active ? idx[beg + q] : 0;
+    int pix = active ? id - band * IJ - p0 : -(lane + 2);
+    for (int it = 0; it < 96; ++it) {
+      const unsigned wonmask = __ballot_sync(0xffffffffu, won);
+      const unsigned und = __ballot_sync(0xffffffffu, active && !won);
+      if (!und) break;
+      const unsigned m = __match_any_sync(0xffffffffu, pix);
+      const int skey = (active || won) ? (((lane >> 3) << 3) | (pix & 7)) : 64 + lane;
+      const unsigned ms = __match_any_sync(0xffffffffu, skey);
+      if (active && !won) {
+        bool ok = (m & wonmask) == 0 && lane == __ffs(m & und) - 1;
+        if (ok && tries < navail) ok = (ms & wonmask) == 0 && lane == __ffs(ms & und) - 1;  // first sweep: free bank group too
+        if (ok) {
+          won = true;
+        } else {
+          ++tries;
+          if (tries >= 2 * navail) {
+            active = false;
+            pix = -(lane + 2);
+          } else {
+            q = cur + (tries % navail);
+            id = idx[beg + q];
+            pix = id - band * IJ - p0;
+          }
+        }
+      }
+    }
+    uint32_t word = (LANE_PAD_LEVEL << 24) | ((uint32_t)band << 15) | pad_pix;
+    if (won) {
+      const int lv = lvl[beg + q];
+      if (q != cur) {  // move the chosen entry to the front of what is left of the row
+        idx[beg + q] = idx[beg + cur];
+        lvl[beg + q] = lvl[beg + cur];
+        idx[beg + cur] = id;
+        lvl[beg + cur] = (uint8_t)lv;
+      }
+      ++cur;
+      word = ((uint32_t)lv << 24) | ((uint32_t)band << 15) | (uint32_t)pix;
+    }
+    if (step < cap) words[out0 + ((int64_t)(step >> 2) * 32 + lane) * LANE_GROUP + (step & 3)] = word;
+    ++step;
+    if (step > cap + 4096) break;  // hopeless: report and stop
+  }
+  // pad the last group
+  const uint32_t padw = (LANE_PAD_LEVEL << 24) | ((uint32_t)band << 15) | pad_pix;
+  while (step & (LANE_GROUP - 1)) {
+    if (step < cap) words[out0 + ((int64_t)(step >> 2) * 32 + lane) * LANE_GROUP + (step & 3)] = padw;
+    ++step;
+  }
+  if (lane == 0) {
+    nrows[s] = step <= cap ? step : cap;
+    if (step > cap) atomicExch(overflow, 1);
+  }
+}
+
 // ---- exclusive scan of int64 counts (in place: counts[i] -> offset, plus total at [n]) ----------
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -248,6 +373,45 @@ extern "C" int qmc_quantize_levels(const float* noisy_dev, int64_t n, const floa
   tab.n = n_bounds;
   for (int i = 0; i < n_bounds; ++i) tab.b[i] = bounds_host[i];
   quantize_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(noisy_dev, n, tab, lvl_out_dev, y_out_dev);
+  count_launch();
+  QMC_CUDA_CHECK(cudaGetLastError());
+  return QMC_OK;
+}
+
+extern "C" int qmc_obs_build_lanes(int32_t* idx_rows_dev, uint8_t* lvl_rows_dev, const int64_t* row_off_dev,
+                                   int B, int K, int IJ, int n_sub, int sub_pixels, int tile_warps,
+                                   const int64_t* stream_off_dev, uint32_t* words_out_dev,
+                                   int32_t* nrows_out_dev, int32_t* overflow_dev, void* stream) {
+  QMC_REQUIRE(idx_rows_dev && lvl_rows_dev && row_off_dev && stream_off_dev && words_out_dev && nrows_out_dev &&
+              overflow_dev, "null argument");
+  QMC_REQUIRE(B > 0 && K > 0 && K <= 256 && IJ > 0 && n_sub > 0, "bad sizes (K must be <= 256)");
+  QMC_REQUIRE(tile_warps > 0 && n_sub % tile_warps == 0 && sub_pixels > 0, "bad tiling");
+  QMC_REQUIRE((int64_t)tile_warps * sub_pixels + 32 <= 32768, "tile of %lld pixels does not fit the 15-bit pixel field",
+              (long long)tile_warps * sub_pixels);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_streams = (int64_t)B * n_sub;
+  const int warps = 4;
+  const int64_t blocks = (n_streams + warps - 1) / warps;
+  QMC_REQUIRE(blocks <= 0x7fffffff, "too many streams");
+  QMC_CUDA_CHECK(cudaMemsetAsync(overflow_dev, 0, sizeof(int32_t), st));
+  const size_t smem = (size_t)warps * K * sizeof(int16_t);
+  const int G = (K + 31) / 32;
+#define QMC_LANES_GO(GG)                                                                                       \
+  obs_lanes_kernel<GG><<<(unsigned)blocks, warps * 32, smem, st>>>(idx_rows_dev, lvl_rows_dev, row_off_dev,     \
+                                                                   n_streams, K, IJ, n_sub, sub_pixels, tile_warps, \
+                                                                   stream_off_dev, words_out_dev, nrows_out_dev,   \
+                                                                   overflow_dev)
+  switch (G) {
+    case 1: QMC_LANES_GO(1); break;
+    case 2: QMC_LANES_GO(2); break;
+    case 3: QMC_LANES_GO(3); break;
+    case 4: QMC_LANES_GO(4); break;
+    case 5: QMC_LANES_GO(5); break;
+    case 6: QMC_LANES_GO(6); break;
+    case 7: QMC_LANES_GO(7); break;
+    default: QMC_LANES_GO(8); break;
+  }
+#undef QMC_LANES_GO
   count_launch();
   QMC_CUDA_CHECK(cudaGetLastError());
   return QMC_OK;

@@ -181,10 +181,11 @@ def qmc_nll(S, C_, Y, Wx, bin_boundaries, noise_std, offset=None, log_domain=Non
 
 
 def make_obs(Y, Wx, K: Optional[int] = None, device=None, *, B: int = 1, R: Optional[int] = None,
-             tiled: Optional[bool] = None, tile_warps: int = 8) -> ObsSet:
+             tiled: Optional[bool] = None, tile_warps: int = 8, lanes: Optional[bool] = None) -> ObsSet:
     """Build the compact observation set of one map (reference shapes ``[K,1,I,J]``) or of a batch
     ``[B,K,...]``.  ``tiled`` (default: batches of >= 64 maps) lays the entries out for the
-    shared-memory kernel; it needs the rank R to size the tiles."""
+    shared-memory kernels; it needs the rank R to size the tiles.  ``lanes`` (default: when
+    32 <= K <= 256 and levels <= 254) additionally re-cuts every warp's stream into per-lane band walks."""
     dev = torch.device(device) if device is not None else (Y.device if Y.is_cuda else torch.device("cuda", torch.cuda.current_device()))
     if K is None:
         K = Y.shape[0] if B == 1 else Y.shape[1]
@@ -194,9 +195,11 @@ def make_obs(Y, Wx, K: Optional[int] = None, device=None, *, B: int = 1, R: Opti
     if tiled:
         if R is None:
             raise ValueError("tiled layout needs R")
-        n_sub, sub, tw = plan_tiles(IJ, K, R, tile_warps)
-        bm = bank_mod_for_rank(R)
+        if lanes is None:
+            lanes = 32 <= K <= 256          # every lane of the warp owns at least one band
+        n_sub, sub, tw = plan_tiles(IJ, K, R, tile_warps, lanes=lanes)
+        bm = 0 if lanes else bank_mod_for_rank(R)
     else:
-        n_sub, sub, tw, bm = 1, IJ, 0, 0
+        n_sub, sub, tw, bm, lanes = 1, IJ, 0, 0, False
     return build_obs(Y.to(dev), None if Wx is None else Wx.to(dev), K, IJ, B, n_sub=n_sub, sub_pixels=sub,
-                     tile_warps=tw, bank_mod=bm)
+                     tile_warps=tw, bank_mod=bm, lanes=bool(lanes))

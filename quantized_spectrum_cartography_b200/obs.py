@@ -20,7 +20,7 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def plan_tiles(IJ: int, K: int, R: int, tile_warps: int = 8, smem_budget: int = 100 * 1024):
+def plan_tiles(IJ: int, K: int, R: int, tile_warps: int = 8, smem_budget: int = 100 * 1024, lanes: bool = False):
     """Choose the pixel sub-tile size for the shared-memory (tiled) kernel.
 
     Returns (n_sub, sub_pixels, tile_warps).  A tile is ``tile_warps`` sub-tiles; its S and gS
@@ -29,8 +29,15 @@ def plan_tiles(IJ: int, K: int, R: int, tile_warps: int = 8, smem_budget: int = 
     RP = 1
     while RP < R:
         RP *= 2
-    wc = tile_warps if tile_warps * K * RP * 4 <= 32 * 1024 else 1     # private gC copies (qmc_gather.cu)
-    fixed = (1 + wc) * K * RP * 4 + tile_warps * (K + 2) * 4 + tile_warps * 32 * RP * 4 + 16
+    if lanes:
+        # the lanes kernel always keeps one private gC copy per warp: use fewer warps if K*R is large
+        while tile_warps > 1 and (1 + tile_warps) * (K + 1) * RP * 4 > smem_budget // 2:
+            tile_warps //= 2
+        wc = tile_warps
+        fixed = (1 + wc) * (K + 1) * RP * 4 + 2 * 32 * RP * 4 + 16
+    else:
+        wc = tile_warps if tile_warps * K * RP * 4 <= 32 * 1024 else 1     # private gC copies (qmc_gather.cu)
+        fixed = (1 + wc) * K * RP * 4 + tile_warps * (K + 2) * 4 + tile_warps * 32 * RP * 4 + 16
     max_tile_pixels = max((smem_budget - fixed) // (2 * RP * 4), tile_warps)
     if IJ <= max_tile_pixels:
         sub = -(-IJ // tile_warps)
@@ -56,10 +63,27 @@ class ObsSet:
     tile_warps: int
     nobs: int
     max_level: int
+    words: "torch.Tensor | None" = None        # lane-stream layout: uint32 words (stored as int32)
+    stream_off: "torch.Tensor | None" = None   # lane-stream layout: int64 [B*n_sub + 1] word offsets
+    nrows: "torch.Tensor | None" = None        # lane-stream layout: int32 [B*n_sub] steps per stream
+
+    @property
+    def lanes(self) -> bool:
+        return self.words is not None
 
     def view(self) -> ObsView:
         return ObsView(self.idx.data_ptr(), self.lvl.data_ptr(), self.row_off.data_ptr(),
-                       self.n_sub, self.sub_pixels)
+                       self.n_sub, self.sub_pixels,
+                       self.words.data_ptr() if self.lanes else None,
+                       self.stream_off.data_ptr() if self.lanes else None,
+                       self.nrows.data_ptr() if self.lanes else None)
+
+    def padding_fraction(self) -> float:
+        """Lane-stream layout: fraction of the walked slots that are padding."""
+        if not self.lanes:
+            return 0.0
+        slots = int(self.nrows.sum().item()) * 32
+        return 1.0 - self.nobs / max(slots, 1)
 
     @property
     def device(self):
@@ -84,7 +108,8 @@ def bank_mod_for_rank(R: int) -> int:
 
 
 def build_obs(Y: torch.Tensor, Wx: torch.Tensor | None, K: int, IJ: int, B: int = 1, *,
-              n_sub: int = 1, sub_pixels: int | None = None, tile_warps: int = 0, bank_mod: int = 0) -> ObsSet:
+              n_sub: int = 1, sub_pixels: int | None = None, tile_warps: int = 0, bank_mod: int = 0,
+              lanes: bool = False) -> ObsSet:
     """(Y, Wx) dense ``[B][K][IJ]`` (any shape with that many elements; the reference's is
     ``[K,1,I,J]``) -> ObsSet on Y's CUDA device.  Y: int64 (reference dtype) or uint8."""
     if not Y.is_cuda:
@@ -114,5 +139,38 @@ def build_obs(Y: torch.Tensor, Wx: torch.Tensor | None, K: int, IJ: int, B: int 
         check(lib.qmc_obs_fill(Yc.data_ptr(), int(Y.dtype == torch.int64), wptr, B, K, IJ, n_sub, sub_pixels,
                                bank_mod, row_off.data_ptr(), idx.data_ptr(), lvl.data_ptr(), _stream()))
         max_level = int(lvl[:nobs].max().item()) if nobs else 0
-    return ObsSet(idx[:nobs] if nobs else idx[:0], lvl[:nobs] if nobs else lvl[:0], row_off, B, K, IJ,
-                  n_sub, sub_pixels, tile_warps, nobs, max_level)
+    obs = ObsSet(idx[:nobs] if nobs else idx[:0], lvl[:nobs] if nobs else lvl[:0], row_off, B, K, IJ,
+                 n_sub, sub_pixels, tile_warps, nobs, max_level)
+    return lane_streams(obs) if lanes else obs
+
+
+def lane_streams(obs: ObsSet) -> ObsSet:
+    """Re-cut a row-ordered observation set (built with ``bank_mod=0``) into the lane-stream layout
+    (see qmc_obs_build_lanes): every lane of a stream's warp walks one band at a time and the 32 entries
+    of a step hit 32 different pixels.  The row-ordered arrays are consumed (permuted in place)."""
+    if obs.K > 256:
+        raise ValueError("the lane-stream layout supports at most 256 bands")
+    if obs.max_level > 254:
+        raise ValueError("the lane-stream layout supports levels 0..254")
+    if obs.tile_warps <= 0:
+        raise ValueError("the lane-stream layout needs a tiled observation set (tile_warps > 0)")
+    dev = obs.device
+    n_streams = obs.B * obs.n_sub
+    per_stream = obs.row_off[:: obs.K][1:] - obs.row_off[:: obs.K][:-1]
+    G = (obs.K + 31) // 32
+    rows_cap = (13 * per_stream * G) // (10 * obs.K) + 8
+    rows_cap = ((rows_cap + 3) // 4) * 4
+    stream_off = torch.zeros(n_streams + 1, dtype=torch.int64, device=dev)
+    stream_off[1:] = torch.cumsum(rows_cap * 32, 0)
+    total = int(stream_off[-1].item())
+    with torch.cuda.device(dev):
+        words = torch.empty(total, dtype=torch.int32, device=dev)
+        nrows = torch.empty(n_streams, dtype=torch.int32, device=dev)
+        overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(lib.qmc_obs_build_lanes(obs.idx.data_ptr(), obs.lvl.data_ptr(), obs.row_off.data_ptr(), obs.B, obs.K,
+                                      obs.IJ, obs.n_sub, obs.sub_pixels, obs.tile_warps, stream_off.data_ptr(),
+                                      words.data_ptr(), nrows.data_ptr(), overflow.data_ptr(), _stream()))
+        if int(overflow.item()):
+            raise RuntimeError("lane-stream layout: a stream exceeded its capacity (pathological band/pixel structure)")
+    return ObsSet(obs.idx, obs.lvl, obs.row_off, obs.B, obs.K, obs.IJ, obs.n_sub, obs.sub_pixels, obs.tile_warps,
+                  obs.nobs, obs.max_level, words, stream_off, nrows)

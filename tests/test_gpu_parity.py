@@ -509,3 +509,82 @@ def test_cuda_graph_solver_matches_eager(q):
         np.testing.assert_allclose(cb.cpu().numpy(), ca.cpu().numpy(), rtol=1e-5)
     for na, nb in zip(a.nmse, b.nmse):
         np.testing.assert_allclose(nb.cpu().numpy(), na.cpu().numpy(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("B,I,J,K,R,levels,log_domain,f,tw,n_tiles", [
+    (5, 51, 51, 64, 4, 2, False, 0.10, 8, 1),      # cfg1/cfg3 geometry
+    (3, 30, 31, 40, 3, 4, True, 0.30, 4, 2),       # K not a multiple of 32, two tiles per map, padded rank
+    (2, 40, 40, 128, 8, 8, True, 0.20, 8, 1),      # cfg2-like
+    (1, 64, 64, 256, 16, 8, False, 0.50, 2, 4),    # cfg4-like bands and rank
+    (4, 23, 17, 33, 1, 2, False, 0.60, 2, 1),      # rank 1, dense sampling
+    (2, 19, 21, 12, 2, 2, False, 0.40, 4, 1),      # fewer bands than lanes: idle lanes walk the dummy band
+    (3, 51, 51, 64, 4, 2, False, 0.01, 8, 1),      # very sparse: bands of 0..3 entries, many band switches per group
+])
+def test_lane_stream_builder_and_kernel(q, B, I, J, K, R, levels, log_domain, f, tw, n_tiles):
+    """The lane-stream observation layout: (a) the real entries of a step have pairwise distinct
+    pixels, every lane walks its bands as contiguous runs, a band belongs to one lane of the stream,
+    padding is level 0xFF on a dummy pixel row, and the entries are exactly those of (Y, Wx);
+    (b) the lanes kernel agrees with the oracle and with the flat kernel."""
+    from quantized_spectrum_cartography_b200 import _lib
+    IJ = I * J
+    S, C, Y, Wx, bb, sigma, off = _random_instance(B, I, J, K, R, f, levels, seed=K + R, log_domain=log_domain)
+    Wx[B - 1, :, : IJ // 3] = 0                      # a ragged map
+    lik = q.make_likelihood(bb, sigma, offset=off)
+    n_sub = tw * n_tiles
+    sub = -(-IJ // n_sub)
+    TP = tw * sub
+    obs = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, B, n_sub=n_sub, sub_pixels=sub, tile_warps=tw, lanes=True)
+    assert obs.lanes and obs.nobs == int(Wx.sum().item())
+    words = obs.words.cpu().numpy().view(np.uint32).astype(np.int64)
+    so = obs.stream_off.cpu().numpy()
+    nr = obs.nrows.cpu().numpy()
+    seen = []
+    for s_id in range(B * n_sub):
+        b, st = divmod(s_id, n_sub)
+        p0 = (st // tw) * TP
+        assert nr[s_id] % 4 == 0 and so[s_id] % 128 == 0
+        blk = words[so[s_id]: so[s_id] + 32 * nr[s_id]].reshape(-1, 32, 4).transpose(0, 2, 1).reshape(-1, 32)   # [step][lane]
+        lv, band, pix = blk >> 24, (blk >> 15) & 0x1FF, blk & 0x7FFF
+        real = lv != 0xFF
+        assert np.all(pix[~real] == TP + np.broadcast_to(np.arange(32), pix.shape)[~real])
+        owner = {}
+        for lane in range(32):
+            runs = band[:, lane][np.r_[True, band[1:, lane] != band[:-1, lane]]] if len(band) else []
+            assert len(set(runs.tolist() if len(band) else [])) == len(runs)            # contiguous runs
+            for k in set(band[real[:, lane], lane].tolist()):
+                assert owner.setdefault(k, lane) == lane                                 # one lane per band
+        for row_real, row_pix in zip(real, pix):
+            v = row_pix[row_real]
+            assert len(set(v.tolist())) == len(v)
+        p = pix[real] + p0
+        assert np.all((p >= st * sub) & (p < (st + 1) * sub))
+        seen.append(np.stack([np.full_like(p, b), band[real] * IJ + p, lv[real]], 1))
+    seen = np.concatenate(seen)
+    order = np.lexsort((seen[:, 1], seen[:, 0]))
+    want_idx = []
+    for b in range(B):
+        i_ref, l_ref = oc.observed_entries(Y[b], Wx[b])
+        want_idx.append(np.stack([np.full_like(i_ref, b), i_ref, l_ref], 1))
+    np.testing.assert_array_equal(seen[order], np.concatenate(want_idx))
+    if f >= 0.1 and K % 32 == 0:                     # every lane owns the same number of bands
+        assert obs.padding_fraction() < 0.35
+    # kernel
+    nll, gS, gC = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik)
+    obs_f = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, B)
+    nll_f, gS_f, gC_f = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs_f, lik, algo=_lib.QMC_ALGO_FLAT)
+    np.testing.assert_allclose(nll.cpu().numpy(), nll_f.cpu().numpy(), rtol=1e-6)
+    assert rel_err(gS.cpu().numpy(), gS_f.cpu().numpy()) < 2e-5
+    assert rel_err(gC.cpu().numpy(), gC_f.cpu().numpy()) < 2e-5
+    for b in (0, B - 1):
+        want = oc.nll_and_grads_fp64(S[b].reshape(R, 1, I, J), C[b], Y[b].reshape(K, 1, I, J), Wx[b].reshape(K, 1, I, J),
+                                     bb, sigma, offset=off, sentinels=off is None)
+        assert nll[b].item() == pytest.approx(want[0], rel=NLL_RTOL)
+        assert rel_err(gS[b].cpu().numpy(), want[1].reshape(R, -1)) < GRAD_RTOL
+        assert rel_err(gC[b].cpu().numpy(), want[2]) < GRAD_RTOL
+    # pixel-major storage (TMA bulk staging) and forward-only
+    S_pm = S.cuda().transpose(1, 2).contiguous().transpose(1, 2)
+    nll_p, gS_p, _ = q.nll_fwd_bwd(S_pm, C.cuda(), obs, lik)
+    np.testing.assert_allclose(nll_p.cpu().numpy(), nll.cpu().numpy(), rtol=1e-12)
+    assert torch.equal(gS_p.contiguous(), gS) or rel_err(gS_p.cpu().numpy(), gS.cpu().numpy()) < 1e-6
+    nll_o, _, _ = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik, want_grad=False)
+    np.testing.assert_allclose(nll_o.cpu().numpy(), nll.cpu().numpy(), rtol=1e-12)
