@@ -89,9 +89,11 @@ typedef struct qmc_obs_view {
   int32_t sub_pixels;  /* pixels per sub-tile */
   /* Lane-stream layout (qmc_obs_build_lanes), NULL otherwise: the entries of every (map, sub-tile)
    * stream re-cut so that each lane of the owning warp walks one band at a time and the 32 entries
-   * of a step hit 32 different pixels.  word = level << 24 | band << 15 | tile-local pixel; level
-   * 0xFF marks padding.  Steps are stored in groups of four, lane-interleaved: word(t, lane) at
-   * stream_off[s] + ((t / 4) * 32 + lane) * 4 + t % 4.  idx/lvl/row_off are not used by the kernel. */
+   * of a step hit 32 different pixels; a lane changes band only at a multiple of four steps.
+   * word: bit 31 = level & 1, bits 24..30 = level >> 1, bits 15..23 = band, bits 0..14 = tile-local
+   * pixel; level 0xFF (bits 24..31 all set) marks padding.  Steps are stored in groups of four,
+   * lane-interleaved: word(t, lane) at stream_off[s] + ((t / 4) * 32 + lane) * 4 + t % 4.
+   * idx/lvl/row_off are not used by the kernel. */
   const uint32_t* words_dev;
   const int64_t* stream_off_dev; /* B*n_sub + 1 word offsets, multiples of 128 */
   const int32_t* nrows_dev;      /* B*n_sub steps per stream, multiples of 4 */
@@ -136,7 +138,7 @@ QMC_API int qmc_obs_fill(const void* y_dev, int y_is_int64, const float* wx_dev,
 /* Re-cut a row-ordered observation set (n_sub, sub_pixels as built by qmc_obs_count_scan/qmc_obs_fill
  * with bank_mod = 0) into the lane-stream layout for tiles of tile_warps sub-tiles.  idx_rows/lvl_rows
  * are used as scratch and come back permuted inside their rows.  stream_off_dev: caller-chosen
- * capacities in words (multiples of 128; 32 * (1.3 * n * ceil(K/32) / K + 8) words for a stream of n
+ * capacities in words (multiples of 128; 32 * (1.3 * n * G / K + 4 * G + 8) words, G = ceil(K/32), for a stream of n
  * entries is ample); nrows_out_dev receives the steps actually used; *overflow_dev is set to 1 if a
  * stream did not fit its capacity.  K <= 256, levels <= 254, tile_warps * sub_pixels + 32 <= 32768. */
 QMC_API int qmc_obs_build_lanes(int32_t* idx_rows_dev, uint8_t* lvl_rows_dev, const int64_t* row_off_dev,

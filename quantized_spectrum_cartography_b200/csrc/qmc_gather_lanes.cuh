@@ -12,29 +12,90 @@ namespace qmc {
 // the entries of ONE band at a time, so C[band] and the band's gC accumulator stay in registers (no
 // shared-memory traffic, no warp reduction, one plain store per (warp, band)); the builder guarantees
 // that the 32 entries of a step hit 32 different pixels, so the gS update is a plain shared-memory
-// read-modify-write.  Per entry the shared-memory pipe sees one S row read and one gS row
-// read-modify-write -- half of what the tiled/matched kernels need -- and the bank groups inside a
-// quarter-warp are distinct wherever the builder had a choice.
-// Shared memory (floats): Ssm[TP+32][RP] | gSsm[TP+32][RP] | Csm[K+1][RP] | gCw[W][K+1][RP]; the 32 extra
-// pixel rows and the extra band row absorb padding words.
+// read-modify-write, and that a lane changes band only at a group (4-step) boundary.  Per entry the
+// shared-memory pipe sees one S row read and one gS row read-modify-write; a padding lane re-reads a
+// row that a real lane of its quarter-warp reads anyway (a broadcast) and its update is predicated off.
+//
+// The warps of a CTA are autonomous: each stages its own S slice (its own TMA bulk copy and
+// mbarrier), zeroes and later writes its own gS slice, and keeps a private gC copy; the only CTA-wide
+// synchronisation is one early barrier after C is staged.  The last warp to finish folds the gC
+// copies and the NLL partials and writes them out.
+// Shared memory (floats): Ssm[TP][RP] | gSsm[TP][RP] | Csm[K+1][RP] | gCw[W][K+1][RP]; band row K is a
+// dummy that absorbs the flush of a lane that owns no band.
+
+// ---- packed fp32x2 arithmetic (FFMA2/FMUL2/FADD2, sm_100) --------------------------------------
+struct f2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ f2 mk2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void un2(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f2 bc2(float x) { return mk2(x, x); }
+
+// ---- predicated shared-memory accesses ------------------------------------------------------------
+// the load leaves its registers undefined when predicated off: only for values that are then stored
+// under the same predicate
+__device__ __forceinline__ float4 lds128_if(uint32_t a, bool p) {
+  float4 v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "r"((int)p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128_if(uint32_t a, float4 v, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+               ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)p) : "memory");
+}
+__device__ __forceinline__ float lds32_if(uint32_t a, bool p) {
+  float v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.f32 %0, [%1];\n\t}" : "=f"(v) : "r"(a), "r"((int)p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32_if(uint32_t a, float v, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" ::"r"(a), "f"(v), "r"((int)p) : "memory");
+}
+
 __device__ __forceinline__ uint4 ldg_u4(const uint4* p) {
   uint4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// lane-stream word (qmc_obs_build_lanes): bit 31 = level & 1, bits 24..30 = level >> 1, bits 15..23 = band,
+// bits 0..14 = tile-local pixel; level 0xFF (bits 24..31 all set) = padding
+__device__ __forceinline__ bool lw_valid(uint32_t w) { return w < 0xFF000000u; }
+__device__ __forceinline__ int lw_level(uint32_t w) { return (int)(((w >> 23) & 0xFEu) | (w >> 31)); }
 
 template <int RP, int EPI, bool LOGD, bool GRAD>
 __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams prm) {
   extern __shared__ __align__(16) float smem[];
   const int W = prm.tile_warps, K = prm.K;
   const int TP = prm.sub_pixels * W;
-  const int TPD = TP + 32;  // + dummy pixel rows
   float* Ssm = smem;
-  float* gSsm = Ssm + (size_t)TPD * RP;
-  float* Csm = gSsm + (GRAD ? (size_t)TPD * RP : 0);
+  float* gSsm = Ssm + (size_t)TP * RP;
+  float* Csm = gSsm + (GRAD ? (size_t)TP * RP : 0);
   float* gCw = Csm + (size_t)(K + 1) * RP;
-  __shared__ uint64_t mbar;
+  __shared__ uint64_t mbar[8];
   __shared__ double wsum[8];
+  __shared__ int done;
 
   const int b = blockIdx.x / prm.tiles_per_map;
   const int tile = blockIdx.x - b * prm.tiles_per_map;
@@ -44,204 +105,286 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   const int nthr = blockDim.x;
   const float* __restrict__ Sb = prm.S + b * prm.sB;
   const float* __restrict__ Cb = prm.C + (int64_t)b * prm.R * K;
+  float* gSb = GRAD ? prm.gS + b * prm.sB : nullptr;
   const bool bulk = (prm.sR == 1 && prm.sP == RP && prm.R == RP && (RP % 4) == 0 &&
-                     ((reinterpret_cast<uintptr_t>(Sb) | (GRAD ? reinterpret_cast<uintptr_t>(prm.gS + b * prm.sB) : 0)) & 15) == 0);
-  if (bulk) {
-    if (threadIdx.x == 0) mbar_init(&mbar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const uint32_t bytes = (uint32_t)np * RP * sizeof(float);
-      mbar_expect_tx(&mbar, bytes);
-      bulk_g2s(Ssm, Sb + (int64_t)p0 * RP, bytes, &mbar);
-    }
-  } else {
-#pragma unroll
-    for (int r = 0; r < RP; ++r)
-      for (int pl = threadIdx.x; pl < np; pl += nthr)
-        Ssm[pl * RP + r] = (r < prm.R) ? __ldg(Sb + r * prm.sR + (int64_t)(p0 + pl) * prm.sP) : 0.0f;
+                     ((reinterpret_cast<uintptr_t>(Sb) | (GRAD ? reinterpret_cast<uintptr_t>(gSb) : 0)) & 15) == 0);
+  // this warp's pixel slice of the tile
+  const int sl0 = min(warp * prm.sub_pixels, np);
+  const int sln = min((warp + 1) * prm.sub_pixels, np) - sl0;
+  float* Sw = Ssm + (size_t)sl0 * RP;
+  float* gSw = gSsm + (size_t)sl0 * RP;
+
+  // ---- prologue: every warp stages its own slice; one CTA barrier for C -------------------------
+  if (bulk && sln > 0 && lane == 0) {
+    mbar_init(&mbar[warp], 1);
+    const uint32_t bytes = (uint32_t)sln * RP * sizeof(float);
+    mbar_expect_tx(&mbar[warp], bytes);
+    bulk_g2s(Sw, Sb + (int64_t)(p0 + sl0) * RP, bytes, &mbar[warp]);
   }
-  for (int i = np * RP + threadIdx.x; i < TPD * RP; i += nthr) Ssm[i] = 0.0f;  // tail + dummy rows
-#pragma unroll
-  for (int r = 0; r < RP; ++r)
-    for (int k = threadIdx.x; k <= K; k += nthr) Csm[k * RP + r] = (r < prm.R && k < K) ? __ldg(Cb + r * K + k) : 0.0f;
-  if (GRAD) {
-    for (int i = threadIdx.x; i < TPD * RP; i += nthr) gSsm[i] = 0.0f;
-    for (int i = threadIdx.x; i < W * (K + 1) * RP; i += nthr) gCw[i] = 0.0f;
+  if (threadIdx.x == 0) done = 0;
+  for (int i = threadIdx.x; i < RP * (K + 1); i += nthr) {  // one coalesced load per thread, transposed into [k][r]
+    const int r = i / (K + 1), k = i - r * (K + 1);
+    Csm[k * RP + r] = (r < prm.R && k < K) ? __ldg(Cb + r * K + k) : 0.0f;
   }
   const int64_t stream = (int64_t)b * prm.n_sub + (int64_t)tile * W + warp;
   const uint4* gp = reinterpret_cast<const uint4*>(prm.words + prm.stream_off[stream]) + lane;
   const int ngroups = prm.nrows[stream] >> 2;
-  // two groups of look-ahead
-  const uint32_t padw = (0xFFu << 24) | ((uint32_t)K << LW_BAND_SHIFT) | (uint32_t)(TP + lane);
-  const uint4 padg = make_uint4(padw, padw, padw, padw);
-  uint4 wa = ngroups > 0 ? ldg_u4(gp) : padg;
-  uint4 wb = ngroups > 1 ? ldg_u4(gp + 32) : padg;
-  __syncthreads();
-  if (bulk) mbar_wait(&mbar, 0);
+  const int last = max(ngroups - 1, 0);
+  // four groups of register look-ahead (the stream is read once, straight from DRAM)
+  uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
+  if (ngroups > 0) {
+    w0 = ldg_u4(gp);
+    w1 = ldg_u4(gp + (size_t)min(1, last) * 32);
+    w2 = ldg_u4(gp + (size_t)min(2, last) * 32);
+    w3 = ldg_u4(gp + (size_t)min(3, last) * 32);
+  }
+  if (!bulk) {
+#pragma unroll
+    for (int r = 0; r < RP; ++r)
+      for (int pl = lane; pl < sln; pl += 32)
+        Sw[pl * RP + r] = (r < prm.R) ? __ldg(Sb + r * prm.sR + (int64_t)(p0 + sl0 + pl) * prm.sP) : 0.0f;
+  }
+  if (GRAD) {
+    if (RP % 4 == 0) {
+      float4* z = reinterpret_cast<float4*>(gSw);
+      for (int i = lane; i < sln * (RP / 4); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4* zc = reinterpret_cast<float4*>(gCw + (size_t)warp * (K + 1) * RP);
+      for (int i = lane; i < (K + 1) * (RP / 4); i += 32) zc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int i = lane; i < sln * RP; i += 32) gSw[i] = 0.0f;
+      float* zc = gCw + (size_t)warp * (K + 1) * RP;
+      for (int i = lane; i < (K + 1) * RP; i += 32) zc[i] = 0.0f;
+    }
+  }
+  __syncthreads();  // Csm and `done` are ready; the slices are private to their warps
+  if (bulk && sln > 0) mbar_wait(&mbar[warp], 0);
+  __syncwarp();
 
   constexpr uint32_t ROWB = RP * sizeof(float);
   const uint32_t S_a = smem_u32(Ssm), C_a = smem_u32(Csm);
   const uint32_t gS_delta = smem_u32(gSsm) - S_a;
-  const uint32_t gC_delta = smem_u32(gCw + (size_t)warp * (K + 1) * RP) - C_a;
+  const uint32_t gC_a = smem_u32(gCw + (size_t)warp * (K + 1) * RP);
 
-  float nll_part = 0.0f;
+  float nll_part = 0.0f;               // generic epilogues: sum of -log P
+  f2 nl2 = mk2(0.0f, 0.0f);            // packed one-bit epilogue: sum of log2 P, two partial sums
   float c[RP], acc[RP];
-  uint32_t cur_key = wa.x & LW_BAND_MASK;  // band bits of the lane's current band
-  auto load_band = [&](uint32_t key) {
+  uint32_t cur_key = (uint32_t)K << LW_BAND_SHIFT;  // dummy band until the first group
+#pragma unroll
+  for (int r = 0; r < RP; ++r) { c[r] = 0.0f; acc[r] = 0.0f; }
+
+  auto switch_band = [&](uint32_t key) {
+    // one plain store per (warp, band): the band is this lane's alone in this stream
+    if (GRAD) {
+      const uint32_t grow = gC_a + (cur_key >> LW_BAND_SHIFT) * ROWB;
+      if (RP % 4 == 0) {
+#pragma unroll
+        for (int r = 0; r < RP; r += 4) sts128(grow + r * 4, make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]));
+      } else {
+#pragma unroll
+        for (int r = 0; r < RP; ++r) sts32(grow + r * 4, acc[r]);
+      }
+    }
+    cur_key = key;
     const uint32_t crow = C_a + (key >> LW_BAND_SHIFT) * ROWB;
     if (RP % 4 == 0) {
 #pragma unroll
       for (int r = 0; r < RP; r += 4) {
-        const float4 c4 = lds128_ro(crow + r * 4);
+        const float4 c4 = lds128(crow + r * 4);
         c[r] = c4.x; c[r + 1] = c4.y; c[r + 2] = c4.z; c[r + 3] = c4.w;
       }
     } else {
 #pragma unroll
-      for (int r = 0; r < RP; ++r) c[r] = lds32_ro(crow + r * 4);
+      for (int r = 0; r < RP; ++r) c[r] = lds32(crow + r * 4);
     }
 #pragma unroll
     for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
   };
-  auto flush_band = [&](uint32_t key) {  // one plain store per (warp, band): the band is this lane's alone
-    if (!GRAD) return;
-    const uint32_t grow = C_a + gC_delta + (key >> LW_BAND_SHIFT) * ROWB;
-    if (RP % 4 == 0) {
-#pragma unroll
-      for (int r = 0; r < RP; r += 4) sts128(grow + r * 4, make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]));
-    } else {
-#pragma unroll
-      for (int r = 0; r < RP; ++r) sts32(grow + r * 4, acc[r]);
-    }
-  };
-  load_band(cur_key);
 
-  // likelihood + gradient scale of NS steps (independent chains, interleaved by the compiler)
-  auto steps = [&](const uint32_t (&w)[4], auto ns_tag, auto switch_tag) {
-    constexpr int NS = decltype(ns_tag)::value;
-    constexpr bool SWITCH = decltype(switch_tag)::value;
-    float g[NS], sv[NS][RP];
-    uint32_t srow[NS];
+  // constants of the packed one-bit epilogue: everything in units scaled by s = sqrt(log2 e), so that
+  // exp(-u^2) = 2^(-(s u)^2) and log P comes out in log2 units
+  constexpr float kS = 1.2011224087864498f;  // sqrt(log2(e))
+  constexpr float ecf[QMC_ERFCX_DEG + 1] = QMC_ERFCX_COEFFS;
+  const f2 nthr2 = bc2(-prm.thr), inva2 = bc2(prm.inv_a * kS);
+  const f2 kg2 = bc2(kInvSqrtPi * prm.inv_a);
+
+  auto group = [&](const uint4 wv) {
+    const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+    const uint32_t key = w[0] & LW_BAND_MASK;
+    if (key != cur_key) switch_band(key);  // lanes change band only at group boundaries
+    float g[4], sv[4][RP];
+    uint32_t srow[4];
+    bool ok[4];
+    float t[4];
 #pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      if (SWITCH) {
-        const uint32_t key = w[j] & LW_BAND_MASK;
-        if (key != cur_key) {
-          flush_band(cur_key);
-          cur_key = key;
-          load_band(key);
-        }
-      }
+    for (int j = 0; j < 4; ++j) {
+      ok[j] = lw_valid(w[j]);
       srow[j] = S_a + (w[j] & LW_PIX_MASK) * ROWB;
       if (RP % 4 == 0) {
 #pragma unroll
         for (int r = 0; r < RP; r += 4) {
-          const float4 s4 = lds128_ro(srow[j] + r * 4);
+          const float4 s4 = lds128_ro(srow[j] + r * 4);  // padding words point at a real lane's row (broadcast)
           sv[j][r] = s4.x; sv[j][r + 1] = s4.y; sv[j][r + 2] = s4.z; sv[j][r + 3] = s4.w;
         }
       } else {
 #pragma unroll
         for (int r = 0; r < RP; ++r) sv[j][r] = lds32_ro(srow[j] + r * 4);
       }
-      float t = 0.0f;
+      if (RP % 2 == 0) {
+        f2 d = mul2(mk2(sv[j][0], sv[j][1]), mk2(c[0], c[1]));
 #pragma unroll
-      for (int r = 0; r < RP; ++r) t = fmaf(sv[j][r], c[r], t);
-      const int lv = (int)(w[j] >> 24);
-      const bool ok = lv != 0xFF;
-      float dxdt;
-      const BinEval ev = eval_entry<EPI, LOGD>(prm, t, (EPI == EPI_ONEBIT) ? (lv & 1) : lv, dxdt);
-      nll_part -= ok ? ev.logp : 0.0f;
-      g[j] = ok ? ev.gx * dxdt : 0.0f;
-      if (GRAD && SWITCH) {
-        // sequential form: finish this step's updates before a later step may change band
-        const uint32_t rs = srow[j] + gS_delta;
-        if (RP % 4 == 0) {
+        for (int r = 2; r < RP; r += 2) d = fma2(mk2(sv[j][r], sv[j][r + 1]), mk2(c[r], c[r + 1]), d);
+        float lo, hi;
+        un2(d, lo, hi);
+        t[j] = lo + hi;
+      } else {
+        t[j] = 0.0f;
 #pragma unroll
-          for (int r = 0; r < RP; r += 4) {
-            float4 v = lds128(rs + r * 4);
-            v.x = fmaf(g[j], c[r], v.x); v.y = fmaf(g[j], c[r + 1], v.y);
-            v.z = fmaf(g[j], c[r + 2], v.z); v.w = fmaf(g[j], c[r + 3], v.w);
-            sts128(rs + r * 4, v);
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < RP; ++r) sts32(rs + r * 4, fmaf(g[j], c[r], lds32(rs + r * 4)));
-        }
-#pragma unroll
-        for (int r = 0; r < RP; ++r) acc[r] = fmaf(g[j], sv[j][r], acc[r]);
-        __syncwarp();
+        for (int r = 0; r < RP; ++r) t[j] = fmaf(sv[j][r], c[r], t[j]);
       }
     }
-    if (GRAD && !SWITCH) {
+    if (EPI == EPI_ONEBIT && !LOGD) {
+      // P = 0.5 erfc(u), u = (x - thr) * (level ? -1 : +1) / a.  Padding: x := huge, level bit set ->
+      // u = -inf -> E = 0, P = 1, log P = 0, g = 0 with no further selects.
 #pragma unroll
-      for (int j = 0; j < NS; ++j) {
+      for (int j = 0; j < 4; j += 2) {
+        const f2 x2 = mk2(ok[j] ? t[j] : 3.0e38f, ok[j + 1] ? t[j + 1] : 3.0e38f);
+        const f2 v2 = mul2(add2(x2, nthr2), inva2);  // s * |u| up to sign
+        float va, vb;
+        un2(v2, va, vb);
+        const f2 t2 = mk2(rcp_approx(fabsf(va) + QMC_ERFCX_C * kS), rcp_approx(fabsf(vb) + QMC_ERFCX_C * kS));
+        const f2 q2 = fma2(t2, bc2(-2.0f * QMC_ERFCX_C * kS), bc2(1.0f));
+        f2 p2 = bc2(-0.5f * kS * ecf[QMC_ERFCX_DEG]);
+#pragma unroll
+        for (int i = QMC_ERFCX_DEG - 1; i >= 0; --i) p2 = fma2(p2, q2, bc2(-0.5f * kS * ecf[i]));
+        const f2 hn2 = mul2(p2, t2);  // -0.5 erfcx(|u|)
+        const f2 w22 = mul2(v2, v2);  // (s u)^2
+        float wa2, wb2, hna, hnb;
+        un2(w22, wa2, wb2);
+        un2(hn2, hna, hnb);
+        const float Ea = ex2_approx(-wa2), Eb = ex2_approx(-wb2);
+        const f2 om2 = fma2(mk2(Ea, Eb), hn2, bc2(1.0f));  // 1 - E * 0.5 erfcx
+        float oma, omb;
+        un2(om2, oma, omb);
+        // sign(u) = sign(v) ^ level bit (bit 31 of the word)
+        const bool posa = (int)(__float_as_uint(va) ^ w[j]) >= 0, posb = (int)(__float_as_uint(vb) ^ w[j + 1]) >= 0;
+        const float arga = posa ? -hna : oma, argb = posb ? -hnb : omb;
+        const f2 lg = mk2(lg2_approx(arga), lg2_approx(argb));
+        const f2 sel = mk2(posa ? wa2 : 0.0f, posb ? wb2 : 0.0f);
+        nl2 = add2(nl2, lg);
+        nl2 = fma2(sel, bc2(-1.0f), nl2);
+        const f2 fr = mul2(mk2(posa ? 1.0f : Ea, posb ? 1.0f : Eb), mk2(rcp_approx(arga), rcp_approx(argb)));
+        const f2 ga = mul2(fr, kg2);
+        float gaa, gab;
+        un2(ga, gaa, gab);
+        g[j] = __uint_as_float(__float_as_uint(gaa) ^ (w[j] & 0x80000000u));
+        g[j + 1] = __uint_as_float(__float_as_uint(gab) ^ (w[j + 1] & 0x80000000u));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int lv = lw_level(w[j]);
+        float dxdt;
+        const BinEval ev = eval_entry<EPI, LOGD>(prm, t[j], (EPI == EPI_ONEBIT) ? (lv & 1) : lv, dxdt);
+        nll_part -= ok[j] ? ev.logp : 0.0f;
+        g[j] = ok[j] ? ev.gx * dxdt : 0.0f;
+      }
+    }
+    if (GRAD) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
         const uint32_t rs = srow[j] + gS_delta;
         if (RP % 4 == 0) {
+          const f2 g2 = bc2(g[j]);
 #pragma unroll
           for (int r = 0; r < RP; r += 4) {
-            float4 v = lds128(rs + r * 4);
-            v.x = fmaf(g[j], c[r], v.x); v.y = fmaf(g[j], c[r + 1], v.y);
-            v.z = fmaf(g[j], c[r + 2], v.z); v.w = fmaf(g[j], c[r + 3], v.w);
-            sts128(rs + r * 4, v);
+            float4 v = lds128(rs + r * 4);  // padding lanes read a real lane's row; only the store is predicated
+            const f2 a = fma2(g2, mk2(c[r], c[r + 1]), mk2(v.x, v.y));
+            const f2 bq = fma2(g2, mk2(c[r + 2], c[r + 3]), mk2(v.z, v.w));
+            un2(a, v.x, v.y);
+            un2(bq, v.z, v.w);
+            sts128_if(rs + r * 4, v, ok[j]);
+          }
+#pragma unroll
+          for (int r = 0; r < RP; r += 2) {
+            const f2 a = fma2(g2, mk2(sv[j][r], sv[j][r + 1]), mk2(acc[r], acc[r + 1]));
+            un2(a, acc[r], acc[r + 1]);
           }
         } else {
 #pragma unroll
-          for (int r = 0; r < RP; ++r) sts32(rs + r * 4, fmaf(g[j], c[r], lds32(rs + r * 4)));
-        }
+          for (int r = 0; r < RP; ++r) sts32_if(rs + r * 4, fmaf(g[j], c[r], lds32(rs + r * 4)), ok[j]);
 #pragma unroll
-        for (int r = 0; r < RP; ++r) acc[r] = fmaf(g[j], sv[j][r], acc[r]);
-        __syncwarp();  // the next step may touch the same pixel from another lane
+          for (int r = 0; r < RP; ++r) acc[r] = fmaf(g[j], sv[j][r], acc[r]);
+        }
       }
+      __syncwarp();  // steps are applied in program order by the converged warp: a later step may touch the same pixel from another lane
     }
   };
 
-  for (int grp = 0; grp < ngroups; ++grp) {
-    const uint4 wv = wa;
-    wa = wb;
-    wb = (grp + 2 < ngroups) ? ldg_u4(gp + (size_t)(grp + 2) * 32) : padg;
-    const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
-    // bands are contiguous runs in a lane's stream: the last word tells whether the group changes band
-    const bool sw = ((wv.w ^ cur_key) & LW_BAND_MASK) != 0;
-    if (__any_sync(0xffffffffu, sw)) {
-      steps(w, std::integral_constant<int, 4>{}, std::true_type{});
-    } else {
-      steps(w, std::integral_constant<int, 4>{}, std::false_type{});
-    }
+  // unrolled by the look-ahead depth so that every buffer keeps its registers (a rotating copy would
+  // wait for the newest load every iteration)
+#define QMC_LANES_STAGE(WX)                                   \
+  if (grp >= ngroups) break;                                  \
+  group(WX);                                                  \
+  WX = ldg_u4(gp + (size_t)min(grp + 4, last) * 32);          \
+  ++grp;
+  for (int grp = 0;;) {
+    QMC_LANES_STAGE(w0)
+    QMC_LANES_STAGE(w1)
+    QMC_LANES_STAGE(w2)
+    QMC_LANES_STAGE(w3)
   }
-  flush_band(cur_key);
+#undef QMC_LANES_STAGE
+  switch_band((uint32_t)K << LW_BAND_SHIFT);  // flush the last band
 
-  double wsumv = warp_sum((double)nll_part);
+  // ---- epilogue: own gS slice out, then the last warp folds gC and the NLL -----------------------
+  if (EPI == EPI_ONEBIT && !LOGD) {
+    float lo, hi;
+    un2(nl2, lo, hi);
+    nll_part = -(lo + hi) * kLn2;
+  }
+  const double wsumv = warp_sum((double)nll_part);
   if (lane == 0) wsum[warp] = wsumv;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double tot = 0.0;
-    for (int i = 0; i < W; ++i) tot += wsum[i];
-    if (prm.tiles_per_map == 1) prm.nll[b] = tot;
-    else atomicAdd(prm.nll + b, tot);
-  }
-  if (!GRAD) return;
-  float* gSb = prm.gS + b * prm.sB;
-  if (bulk) {
-    fence_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0) bulk_s2g(gSb + (int64_t)p0 * RP, gSsm, (uint32_t)np * RP * sizeof(float));
-  } else {
+  if (GRAD && sln > 0) {
+    if (bulk) {
+      fence_async_smem();  // generic-proxy writes to the slice -> visible to the bulk-copy engine
+      __syncwarp();
+      if (lane == 0) bulk_s2g(gSb + (int64_t)(p0 + sl0) * RP, gSw, (uint32_t)sln * RP * sizeof(float));
+    } else {
+      __syncwarp();
 #pragma unroll
-    for (int r = 0; r < RP; ++r)
-      if (r < prm.R)
-        for (int pl = threadIdx.x; pl < np; pl += nthr) gSb[r * prm.sR + (int64_t)(p0 + pl) * prm.sP] = gSsm[pl * RP + r];
-  }
-  float* gCb = prm.gC + (int64_t)b * prm.R * K;
-#pragma unroll
-  for (int r = 0; r < RP; ++r) {
-    if (r >= prm.R) break;
-    for (int k = threadIdx.x; k < K; k += nthr) {
-      float v = 0.0f;
-      for (int w2 = 0; w2 < W; ++w2) v += gCw[((size_t)w2 * (K + 1) + k) * RP + r];
-      if (prm.tiles_per_map == 1) gCb[r * K + k] = v;
-      else atomicAdd(gCb + r * K + k, v);
+      for (int r = 0; r < RP; ++r)
+        if (r < prm.R)
+          for (int pl = lane; pl < sln; pl += 32) gSb[r * prm.sR + (int64_t)(p0 + sl0 + pl) * prm.sP] = gSw[pl * RP + r];
     }
   }
-  if (bulk && threadIdx.x == 0) bulk_wait_all();
+  __threadfence_block();
+  __syncwarp();
+  int prev = 0;
+  if (lane == 0) prev = atomicAdd(&done, 1);
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  if (prev == W - 1) {
+    __threadfence_block();
+    if (lane == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < W; ++i) tot += wsum[i];
+      if (prm.tiles_per_map == 1) prm.nll[b] = tot;
+      else atomicAdd(prm.nll + b, tot);
+    }
+    if (GRAD) {
+      float* gCb = prm.gC + (int64_t)b * prm.R * K;
+#pragma unroll
+      for (int r = 0; r < RP; ++r) {
+        if (r >= prm.R) break;
+        for (int k = lane; k < K; k += 32) {
+          float v = 0.0f;
+          for (int w2 = 0; w2 < W; ++w2) v += gCw[((size_t)w2 * (K + 1) + k) * RP + r];
+          if (prm.tiles_per_map == 1) gCb[r * K + k] = v;
+          else atomicAdd(gCb + r * K + k, v);
+        }
+      }
+    }
+  }
+  if (GRAD && bulk && sln > 0 && lane == 0) bulk_wait_all();  // the slice must stay alive until the engine has read it
 }
 
 template <int RP, int EPI, bool LOGD, bool GRAD>

@@ -153,11 +153,39 @@ __global__ void obs_fill_kernel(const YT* __restrict__ y, const float* __restric
 // from every lane; the entries of a step have pairwise distinct pixels (hard: the kernel updates gS
 // rows without atomics) and, where the lane still has a choice, distinct shared-memory bank groups
 // inside each quarter-warp (soft).  A lane that cannot comply, or has nothing left, emits a padding
-// word.  Word = level << 24 | band << 15 | tile-local pixel; padding = 0xFF << 24 | band << 15 |
-// (tile pixels + lane), i.e. a dummy pixel row private to the lane.  Steps are stored in groups of
-// four, lane-interleaved: word(t, lane) at ((t / 4) * 32 + lane) * 4 + t % 4.
+// word; a lane changes band only at a multiple of four steps.  Word: bit 31 = level & 1, bits 24..30 =
+// level >> 1, bits 15..23 = band, bits 0..14 = tile-local pixel; padding has bits 24..31 all set (level
+// 0xFF) and carries the lane's current band.  Steps are stored in groups of four, lane-interleaved:
+// word(t, lane) at ((t / 4) * 32 + lane) * 4 + t % 4.
 constexpr int LANE_GROUP = 4;
 constexpr uint32_t LANE_PAD_LEVEL = 0xFFu;
+
+// Bank-group assignment inside one quarter-warp: lane i may take bank group r (pixel row mod 8) if it
+// still has a candidate pixel in that group (byte r of cnt[i] > 0).  Maximum bipartite matching by
+// augmenting paths (8 x 8), each lane trying its best-stocked groups first so that the groups it keeps
+// for later steps stay diverse.  owner[r] = lane of the quarter that takes group r, or -1.
+__device__ bool lanes_augment(int i, const unsigned long long* cnt, int* owner, unsigned& visited) {
+  unsigned cand = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if ((cnt[i] >> (8 * r)) & 0xFFull) cand |= 1u << r;
+  cand &= ~visited;
+  while (cand) {
+    int best = 0, bc = -1;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int cr = (int)((cnt[i] >> (8 * r)) & 0xFFull);
+      if (((cand >> r) & 1u) && cr > bc) { bc = cr; best = r; }
+    }
+    cand &= ~(1u << best);
+    visited |= 1u << best;
+    if (owner[best] < 0 || lanes_augment(owner[best], cnt, owner, visited)) {
+      owner[best] = i;
+      return true;
+    }
+  }
+  return false;
+}
 
 template <int G>
 __global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict__ lvl,
@@ -187,62 +215,98 @@ __global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict_
   }
   __syncwarp();
   int bands[G];
+  int left = 0;  // entries this lane still has to emit
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const int r = (g & 1) ? 32 * g + 31 - lane : 32 * g + lane;
     bands[g] = r < K ? band_of_rank[r] : -1;
+    if (bands[g] >= 0) left += (int)(row_off[row0 + bands[g] + 1] - row_off[row0 + bands[g]]);
   }
   int g = -1, band = K, cur = 0, end = 0;  // band K: the dummy band of a lane that owns nothing
+  unsigned long long cnt = 0;              // candidates left per bank group, for band cnt_band
+  int cnt_band = -1;
   const int64_t out0 = stream_off[s];
   const int cap = (int)((stream_off[s + 1] - out0) >> 5);
-  const uint32_t pad_pix = (uint32_t)(TP + lane);
   int step = 0;
-  while (true) {
-    // move on to the lane's next non-empty band
-    while (cur >= end && g < G) {
-      ++g;
-      int nb = -1;
+  while (__any_sync(0xffffffffu, left > 0)) {
+    // move on to the lane's next non-empty band -- only at a group boundary, so that the gather
+    // kernel sees one band per lane and group
+    if ((step & (LANE_GROUP - 1)) == 0) {
+      while (cur >= end && g < G) {
+        ++g;
+        int nb = -1;
 #pragma unroll
-      for (int gg = 0; gg < G; ++gg)
-        if (gg == g) nb = bands[gg];
-      if (g < G && nb >= 0) {
-        const int c0 = (int)(row_off[row0 + nb] - beg), e0 = (int)(row_off[row0 + nb + 1] - beg);
-        if (e0 > c0) { band = nb; cur = c0; end = e0; }
+        for (int gg = 0; gg < G; ++gg)
+          if (gg == g) nb = bands[gg];
+        if (g < G && nb >= 0) {
+          const int c0 = (int)(row_off[row0 + nb] - beg), e0 = (int)(row_off[row0 + nb + 1] - beg);
+          if (e0 > c0) { band = nb; cur = c0; end = e0; }
+        }
       }
     }
     const bool has = cur < end;
-    if (!__any_sync(0xffffffffu, has)) break;
-    const int navail = end - cur;
+    // per-bank-group counts of the lane's remaining candidates (8 x 8 bits, saturating at 255; a
+    // saturated field is recounted after the next take)
+    if (has && cnt_band != band) {
+      cnt = 0;
+      for (int qq = cur; qq < end; ++qq) {
+        const int r = (idx[beg + qq] - band * IJ - p0) & 7;
+        if (((cnt >> (8 * r)) & 0xFFull) < 255) cnt += 1ull << (8 * r);
+      }
+      cnt_band = band;
+    }
+    // matching of the quarter-warp's lanes to bank groups (every lane of the quarter computes the same)
+    unsigned long long qc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qc[i] = __shfl_sync(0xffffffffu, has ? cnt : 0ull, (lane & 24) + i);
+    int owner[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) owner[r] = -1;
+    for (int i = 0; i < 8; ++i) {
+      unsigned visited = 0;
+      if (qc[i]) lanes_augment(i, qc, owner, visited);
+    }
+    int want = -1;  // the bank group this lane should use in this step
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (owner[r] == (lane & 7)) want = r;
+    // pick a pixel: pass 0 walks the candidates of group `want`, pass 1 any candidate; a candidate is
+    // taken if no other lane of the warp holds the same pixel (hard)
     bool active = has, won = false;
-    int tries = 0, q = cur;
-    int id = active ? idx[beg + q] : 0;
-    int pix = active ? id - band * IJ - p0 : -(lane + 2);
-    for (int it = 0; it < 96; ++it) {
+    int pass = want >= 0 ? 0 : 1, q = cur - 1, id = 0, pix = -(lane + 2);
+    auto advance = [&]() {  // next candidate of the current pass, or give up
+      while (active) {
+        ++q;
+        if (q >= end) {
+          if (pass == 1) { active = false; pix = -(lane + 2); break; }
+          pass = 1;
+          q = cur - 1;
+          continue;
+        }
+        id = idx[beg + q];
+        pix = id - band * IJ - p0;
+        if (pass == 1 || (pix & 7) == want) break;
+      }
+    };
+    advance();
+    for (int it = 0; it < 4 * 96; ++it) {
       const unsigned wonmask = __ballot_sync(0xffffffffu, won);
       const unsigned und = __ballot_sync(0xffffffffu, active && !won);
       if (!und) break;
       const unsigned m = __match_any_sync(0xffffffffu, pix);
-      const int skey = (active || won) ? (((lane >> 3) << 3) | (pix & 7)) : 64 + lane;
-      const unsigned ms = __match_any_sync(0xffffffffu, skey);
       if (active && !won) {
-        bool ok = (m & wonmask) == 0 && lane == __ffs(m & und) - 1;
-        if (ok && tries < navail) ok = (ms & wonmask) == 0 && lane == __ffs(ms & und) - 1;  // first sweep: free bank group too
-        if (ok) {
-          won = true;
-        } else {
-          ++tries;
-          if (tries >= 2 * navail) {
-            active = false;
-            pix = -(lane + 2);
-          } else {
-            q = cur + (tries % navail);
-            id = idx[beg + q];
-            pix = id - band * IJ - p0;
-          }
-        }
+        if ((m & wonmask) == 0 && lane == __ffs(m & und) - 1) won = true;
+        else advance();
       }
     }
-    uint32_t word = (LANE_PAD_LEVEL << 24) | ((uint32_t)band << 15) | pad_pix;
+    if (!won) pix = -(lane + 2);
+    // padding re-reads the S row of a real lane of the same quarter-warp (same address: no extra
+    // shared-memory wavefront); its updates are predicated off in the kernel
+    const unsigned wonmask = __ballot_sync(0xffffffffu, won);
+    const unsigned wonq = wonmask & (0xffu << (lane & 24));
+    const int srcl = wonq ? __ffs(wonq) - 1 : (wonmask ? __ffs(wonmask) - 1 : lane);
+    const int padpix = __shfl_sync(0xffffffffu, pix, srcl);
+    uint32_t word = (LANE_PAD_LEVEL << 24) | ((uint32_t)band << 15) | (uint32_t)(wonmask ? padpix : 0);
     if (won) {
       const int lv = lvl[beg + q];
       if (q != cur) {  // move the chosen entry to the front of what is left of the row
@@ -252,14 +316,17 @@ __global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict_
         lvl[beg + cur] = (uint8_t)lv;
       }
       ++cur;
-      word = ((uint32_t)lv << 24) | ((uint32_t)band << 15) | (uint32_t)pix;
+      --left;
+      if (((cnt >> (8 * (pix & 7))) & 0xFFull) == 255) cnt_band = -1;  // saturated: recount
+      else cnt -= 1ull << (8 * (pix & 7));
+      word = ((uint32_t)(lv & 1) << 31) | ((uint32_t)(lv >> 1) << 24) | ((uint32_t)band << 15) | (uint32_t)pix;
     }
     if (step < cap) words[out0 + ((int64_t)(step >> 2) * 32 + lane) * LANE_GROUP + (step & 3)] = word;
     ++step;
     if (step > cap + 4096) break;  // hopeless: report and stop
   }
   // pad the last group
-  const uint32_t padw = (LANE_PAD_LEVEL << 24) | ((uint32_t)band << 15) | pad_pix;
+  const uint32_t padw = (LANE_PAD_LEVEL << 24) | ((uint32_t)band << 15);
   while (step & (LANE_GROUP - 1)) {
     if (step < cap) words[out0 + ((int64_t)(step >> 2) * 32 + lane) * LANE_GROUP + (step & 3)] = padw;
     ++step;

@@ -158,7 +158,7 @@ def lane_streams(obs: ObsSet) -> ObsSet:
     n_streams = obs.B * obs.n_sub
     per_stream = obs.row_off[:: obs.K][1:] - obs.row_off[:: obs.K][:-1]
     G = (obs.K + 31) // 32
-    rows_cap = (13 * per_stream * G) // (10 * obs.K) + 8
+    rows_cap = (13 * per_stream * G) // (10 * obs.K) + 4 * G + 8
     rows_cap = ((rows_cap + 3) // 4) * 4
     stream_off = torch.zeros(n_streams + 1, dtype=torch.int64, device=dev)
     stream_off[1:] = torch.cumsum(rows_cap * 32, 0)

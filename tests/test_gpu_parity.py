@@ -523,7 +523,7 @@ def test_cuda_graph_solver_matches_eager(q):
 def test_lane_stream_builder_and_kernel(q, B, I, J, K, R, levels, log_domain, f, tw, n_tiles):
     """The lane-stream observation layout: (a) the real entries of a step have pairwise distinct
     pixels, every lane walks its bands as contiguous runs, a band belongs to one lane of the stream,
-    padding is level 0xFF on a dummy pixel row, and the entries are exactly those of (Y, Wx);
+    a lane changes band only at group boundaries, padding is level 0xFF, and the entries are exactly those of (Y, Wx);
     (b) the lanes kernel agrees with the oracle and with the flat kernel."""
     from quantized_spectrum_cartography_b200 import _lib
     IJ = I * J
@@ -544,9 +544,10 @@ def test_lane_stream_builder_and_kernel(q, B, I, J, K, R, levels, log_domain, f,
         p0 = (st // tw) * TP
         assert nr[s_id] % 4 == 0 and so[s_id] % 128 == 0
         blk = words[so[s_id]: so[s_id] + 32 * nr[s_id]].reshape(-1, 32, 4).transpose(0, 2, 1).reshape(-1, 32)   # [step][lane]
-        lv, band, pix = blk >> 24, (blk >> 15) & 0x1FF, blk & 0x7FFF
+        lv, band, pix = (((blk >> 24) & 0x7F) << 1) | (blk >> 31), (blk >> 15) & 0x1FF, blk & 0x7FFF
         real = lv != 0xFF
-        assert np.all(pix[~real] == TP + np.broadcast_to(np.arange(32), pix.shape)[~real])
+        g4 = band.reshape(-1, 4, 32)
+        assert np.all(g4 == g4[:, :1, :])                                                # one band per lane and group
         owner = {}
         for lane in range(32):
             runs = band[:, lane][np.r_[True, band[1:, lane] != band[:-1, lane]]] if len(band) else []
