@@ -97,6 +97,8 @@ typedef struct qmc_obs_view {
   const uint32_t* words_dev;
   const int64_t* stream_off_dev; /* B*n_sub + 1 word offsets, multiples of 128 */
   const int32_t* nrows_dev;      /* B*n_sub steps per stream, multiples of 4 */
+  int64_t stream_stride;         /* > 0: stream s starts at word s * stream_stride (a multiple of 128) and
+                                    stream_off_dev is not read -- lets a CTA prefetch a later CTA's data */
 } qmc_obs_view_t;
 
 QMC_API int qmc_abi_version(void);

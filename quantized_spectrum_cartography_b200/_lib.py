@@ -29,7 +29,8 @@ class ObsView(C.Structure):
     """qmc_obs_view_t"""
     _fields_ = [("idx_dev", C.c_void_p), ("lvl_dev", C.c_void_p), ("row_off_dev", C.c_void_p),
                 ("n_sub", C.c_int32), ("sub_pixels", C.c_int32),
-                ("words_dev", C.c_void_p), ("stream_off_dev", C.c_void_p), ("nrows_dev", C.c_void_p)]
+                ("words_dev", C.c_void_p), ("stream_off_dev", C.c_void_p), ("nrows_dev", C.c_void_p),
+                ("stream_stride", C.c_int64)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float

@@ -39,7 +39,8 @@ extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, in
                                       float* gC_out_dev, void* stream) {
   QMC_REQUIRE(S_dev && C_dev && obs && lik && nll_out_dev, "null argument");
   const bool lanes = obs->words_dev != nullptr;
-  QMC_REQUIRE(lanes ? (obs->stream_off_dev && obs->nrows_dev) : (obs->idx_dev && obs->lvl_dev && obs->row_off_dev),
+  QMC_REQUIRE(lanes ? ((obs->stream_off_dev || obs->stream_stride > 0) && obs->nrows_dev)
+                    : (obs->idx_dev && obs->lvl_dev && obs->row_off_dev),
               "null observation arrays");
   QMC_REQUIRE(B > 0 && IJ > 0 && K > 0 && R > 0, "bad sizes B=%d IJ=%d K=%d R=%d", B, IJ, K, R);
   QMC_REQUIRE(R <= QMC_MAX_RANK, "rank %d > %d", R, QMC_MAX_RANK);
@@ -56,6 +57,8 @@ extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, in
   prm.S = S_dev; prm.sB = s_stride_b; prm.sR = s_stride_r; prm.sP = s_stride_p;
   prm.C = C_dev; prm.idx = obs->idx_dev; prm.lvl = obs->lvl_dev; prm.row_off = obs->row_off_dev;
   prm.words = obs->words_dev; prm.stream_off = obs->stream_off_dev; prm.nrows = obs->nrows_dev;
+  prm.stream_stride = lanes ? obs->stream_stride : 0;
+  prm.lookahead = 0;
   prm.nll = nll_out_dev; prm.gS = gS_out_dev; prm.gC = gC_out_dev;
   prm.n_sub = obs->n_sub; prm.sub_pixels = obs->sub_pixels;
   prm.B = B; prm.IJ = IJ; prm.K = K; prm.R = R;
@@ -108,6 +111,18 @@ extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, in
                 obs->sub_pixels * tile_warps, RP, tile_warps);
     prm.tile_warps = tile_warps;
     prm.tiles_per_map = obs->n_sub / tile_warps;
+    {
+      int dev = 0, sms = 0;
+      QMC_CUDA_CHECK(cudaGetDevice(&dev));
+      QMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      const size_t per_cta = lanes_smem_bytes(K, RP, obs->sub_pixels, tile_warps, grad) + 1024 + 256;
+      int per_sm = (int)((228 * 1024) / per_cta);
+      per_sm = per_sm < 1 ? 1 : per_sm;
+      const int by_threads = 2048 / (tile_warps * 32), by_regs = 65536 / (128 * tile_warps * 32);
+      per_sm = per_sm < by_threads ? per_sm : by_threads;
+      per_sm = per_sm < (by_regs < 1 ? 1 : by_regs) ? per_sm : (by_regs < 1 ? 1 : by_regs);
+      prm.lookahead = sms * per_sm;
+    }
   } else if (algo == QMC_ALGO_TILED) {
     QMC_REQUIRE(tile_warps > 0 && tile_warps <= 8, "tile_warps %d out of range [1, 8]", tile_warps);
     QMC_REQUIRE(obs->n_sub % tile_warps == 0, "n_sub %d is not a multiple of tile_warps %d", obs->n_sub, tile_warps);

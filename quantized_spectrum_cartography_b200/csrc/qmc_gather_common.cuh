@@ -18,6 +18,8 @@ struct GatherParams {
   const uint32_t* words;      // lane-stream layout (qmc_obs_build_lanes)
   const int64_t* stream_off;  // lane-stream layout: first word of every (map, sub-tile) stream
   const int32_t* nrows;       // lane-stream layout: steps per stream (multiple of 4)
+  int64_t stream_stride;      // lane-stream layout: > 0 = uniform stream capacity in words (no table look-up)
+  int lookahead;              // lanes kernel: CTAs resident on the device (prefetch distance in CTAs)
   double* nll;
   float* gS;
   float* gC;
@@ -139,7 +141,7 @@ constexpr uint32_t LW_BAND_MASK = 0x00FF8000u;
 constexpr int LW_BAND_SHIFT = 15;
 
 static size_t lanes_smem_bytes(int K, int RP, int sub_pixels, int W, bool grad) {
-  const size_t TP = (size_t)sub_pixels * W + 32;
+  const size_t TP = (size_t)sub_pixels * W;
   size_t fl = TP * RP + (size_t)(K + 1) * RP;
   if (grad) fl += TP * RP + (size_t)W * (K + 1) * RP;
   return fl * sizeof(float) + 16;

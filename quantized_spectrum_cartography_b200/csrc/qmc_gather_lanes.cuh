@@ -122,21 +122,41 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     bulk_g2s(Sw, Sb + (int64_t)(p0 + sl0) * RP, bytes, &mbar[warp]);
   }
   if (threadIdx.x == 0) done = 0;
-  for (int i = threadIdx.x; i < RP * (K + 1); i += nthr) {  // one coalesced load per thread, transposed into [k][r]
-    const int r = i / (K + 1), k = i - r * (K + 1);
-    Csm[k * RP + r] = (r < prm.R && k < K) ? __ldg(Cb + r * K + k) : 0.0f;
-  }
+  // every global load of the prologue is issued before anything waits on one of them (the warp issues in
+  // order: a store of loaded data would hold back the loads behind it for a full memory round trip)
   const int64_t stream = (int64_t)b * prm.n_sub + (int64_t)tile * W + warp;
-  const uint4* gp = reinterpret_cast<const uint4*>(prm.words + prm.stream_off[stream]) + lane;
-  const int ngroups = prm.nrows[stream] >> 2;
-  const int last = max(ngroups - 1, 0);
-  // four groups of register look-ahead (the stream is read once, straight from DRAM)
-  uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
-  if (ngroups > 0) {
-    w0 = ldg_u4(gp);
-    w1 = ldg_u4(gp + (size_t)min(1, last) * 32);
-    w2 = ldg_u4(gp + (size_t)min(2, last) * 32);
-    w3 = ldg_u4(gp + (size_t)min(3, last) * 32);
+  const uint4* gp = reinterpret_cast<const uint4*>(
+                        prm.words + (prm.stream_stride > 0 ? stream * prm.stream_stride : prm.stream_off[stream])) + lane;
+  // four groups of register look-ahead (the stream is read once, straight from DRAM); every stream has
+  // room for at least four groups, so the first loads need not know its length
+  uint4 w0 = ldg_u4(gp), w1 = ldg_u4(gp + 32), w2 = ldg_u4(gp + 64), w3 = ldg_u4(gp + 96);
+  const int nrows_v = __ldg(prm.nrows + stream);
+  const int cn = RP * (K + 1);
+  float cv0 = 0.0f, cv1 = 0.0f;  // C staged as [k][r]: element i -> (r = i / (K+1), k = i % (K+1))
+  {
+    const int i0 = threadIdx.x, i1 = threadIdx.x + nthr;
+    const int r0 = i0 / (K + 1), k0 = i0 - r0 * (K + 1), r1 = i1 / (K + 1), k1 = i1 - r1 * (K + 1);
+    if (i0 < cn && r0 < prm.R && k0 < K) cv0 = __ldg(Cb + r0 * K + k0);
+    if (i1 < cn && r1 < prm.R && k1 < K) cv1 = __ldg(Cb + r1 * K + k1);
+  }
+  // pull the first bytes the CTA that will follow this one on its SM needs (S slice, C, head of the
+  // stream) into L2 now, so that its prologue does not wait on DRAM
+  if (prm.stream_stride > 0 && prm.lookahead > 0 && (int64_t)blockIdx.x + prm.lookahead < (int64_t)gridDim.x) {
+    const int nb = blockIdx.x + prm.lookahead;
+    const int b2 = nb / prm.tiles_per_map, tile2 = nb - b2 * prm.tiles_per_map;
+    const int64_t stream2 = (int64_t)b2 * prm.n_sub + (int64_t)tile2 * W + warp;
+    if (lane < 16) prefetch_l2(reinterpret_cast<const char*>(prm.words + stream2 * prm.stream_stride) + lane * 128);
+    if (lane == 16) prefetch_l2(prm.nrows + stream2);
+    if (warp == 0 && lane >= 24) {
+      const char* c2 = reinterpret_cast<const char*>(prm.C + (int64_t)b2 * prm.R * K);
+      for (int o = (lane - 24) * 128; o < prm.R * K * 4; o += 8 * 128) prefetch_l2(c2 + o);
+    }
+    if (bulk) {
+      const int np2 = min(TP, prm.IJ - tile2 * TP);
+      const int s20 = min(warp * prm.sub_pixels, np2), s2n = min((warp + 1) * prm.sub_pixels, np2) - s20;
+      const char* s2 = reinterpret_cast<const char*>(prm.S + b2 * prm.sB + (int64_t)(tile2 * TP + s20) * RP);
+      for (int o = lane * 128; o < s2n * RP * 4; o += 32 * 128) prefetch_l2(s2 + o);
+    }
   }
   if (!bulk) {
 #pragma unroll
@@ -156,6 +176,17 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       for (int i = lane; i < (K + 1) * RP; i += 32) zc[i] = 0.0f;
     }
   }
+  {
+    const int i0 = threadIdx.x, i1 = threadIdx.x + nthr;
+    if (i0 < cn) Csm[(i0 % (K + 1)) * RP + i0 / (K + 1)] = cv0;
+    if (i1 < cn) Csm[(i1 % (K + 1)) * RP + i1 / (K + 1)] = cv1;
+    for (int i = threadIdx.x + 2 * nthr; i < cn; i += nthr) {
+      const int r = i / (K + 1), k = i - r * (K + 1);
+      Csm[k * RP + r] = (r < prm.R && k < K) ? __ldg(Cb + r * K + k) : 0.0f;
+    }
+  }
+  const int ngroups = nrows_v >> 2;
+  const int last = max(ngroups - 1, 0);
   __syncthreads();  // Csm and `done` are ready; the slices are private to their warps
   if (bulk && sln > 0) mbar_wait(&mbar[warp], 0);
   __syncwarp();

@@ -66,6 +66,7 @@ class ObsSet:
     words: "torch.Tensor | None" = None        # lane-stream layout: uint32 words (stored as int32)
     stream_off: "torch.Tensor | None" = None   # lane-stream layout: int64 [B*n_sub + 1] word offsets
     nrows: "torch.Tensor | None" = None        # lane-stream layout: int32 [B*n_sub] steps per stream
+    stream_stride: int = 0                     # lane-stream layout: > 0 when every stream has the same capacity
 
     @property
     def lanes(self) -> bool:
@@ -76,7 +77,8 @@ class ObsSet:
                        self.n_sub, self.sub_pixels,
                        self.words.data_ptr() if self.lanes else None,
                        self.stream_off.data_ptr() if self.lanes else None,
-                       self.nrows.data_ptr() if self.lanes else None)
+                       self.nrows.data_ptr() if self.lanes else None,
+                       self.stream_stride if self.lanes else 0)
 
     def padding_fraction(self) -> float:
         """Lane-stream layout: fraction of the walked slots that are padding."""
@@ -159,10 +161,12 @@ def lane_streams(obs: ObsSet) -> ObsSet:
     per_stream = obs.row_off[:: obs.K][1:] - obs.row_off[:: obs.K][:-1]
     G = (obs.K + 31) // 32
     rows_cap = (13 * per_stream * G) // (10 * obs.K) + 4 * G + 8
-    rows_cap = ((rows_cap + 3) // 4) * 4
-    stream_off = torch.zeros(n_streams + 1, dtype=torch.int64, device=dev)
-    stream_off[1:] = torch.cumsum(rows_cap * 32, 0)
-    total = int(stream_off[-1].item())
+    rows_cap = torch.clamp(((rows_cap + 3) // 4) * 4, min=16)     # the kernel loads the first four groups blindly
+    # one capacity for all streams (the largest): a stream's address then needs no table look-up, and a
+    # CTA can prefetch the data of the CTA that will follow it on its SM
+    stride = int(rows_cap.max().item()) * 32 if n_streams else 128
+    stream_off = torch.arange(n_streams + 1, dtype=torch.int64, device=dev) * stride
+    total = n_streams * stride
     with torch.cuda.device(dev):
         words = torch.empty(total, dtype=torch.int32, device=dev)
         nrows = torch.empty(n_streams, dtype=torch.int32, device=dev)
@@ -173,4 +177,4 @@ def lane_streams(obs: ObsSet) -> ObsSet:
         if int(overflow.item()):
             raise RuntimeError("lane-stream layout: a stream exceeded its capacity (pathological band/pixel structure)")
     return ObsSet(obs.idx, obs.lvl, obs.row_off, obs.B, obs.K, obs.IJ, obs.n_sub, obs.sub_pixels, obs.tile_warps,
-                  obs.nobs, obs.max_level, words, stream_off, nrows)
+                  obs.nobs, obs.max_level, words, stream_off, nrows, stride)
