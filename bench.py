@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-solver", action="store_true")
     ap.add_argument("--tile-warps", type=int, default=8)
-    ap.add_argument("--smem-budget-kb", type=int, default=100)
+    ap.add_argument("--smem-budget-kb", type=int, default=110)
     ap.add_argument("--obs-layout", default="lanes", choices=["lanes", "rows"],
                     help="lanes: per-lane band walks, conflict-free steps (default); rows: band rows per sub-tile")
     ap.add_argument("--bank-mod", type=int, default=-1, help="-1: conflict-free order for the rank; 0: pixel order")
@@ -111,7 +111,7 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # workload
 # -------------------------------------------------------------------------------------------------
-def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_budget_kb: int = 100, bank_mod: int = -1,
+def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_budget_kb: int = 110, bank_mod: int = -1,
                    lanes: bool = True):
     """cfg3 on one GPU: synthetic maps, one-bit observations, tiled compact observation set.
     Seeds: `seed` data, `seed+1` noise and mask."""

@@ -140,10 +140,12 @@ constexpr uint32_t LW_PIX_MASK = 0x7FFFu;
 constexpr uint32_t LW_BAND_MASK = 0x00FF8000u;
 constexpr int LW_BAND_SHIFT = 15;
 
+constexpr int LANES_DEPTH = 4;  // groups of stream look-ahead per warp (power of two)
 static size_t lanes_smem_bytes(int K, int RP, int sub_pixels, int W, bool grad) {
   const size_t TP = (size_t)sub_pixels * W;
   size_t fl = TP * RP + (size_t)(K + 1) * RP;
   if (grad) fl += TP * RP + (size_t)W * (K + 1) * RP;
+  fl += (size_t)W * LANES_DEPTH * 32 * 4;  // stream ring
   return fl * sizeof(float) + 16;
 }
 // per-family launchers, one explicit instantiation per padded rank (qmc_gather_inst.cu)

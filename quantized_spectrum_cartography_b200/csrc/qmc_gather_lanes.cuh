@@ -20,7 +20,7 @@ namespace qmc {
 // mbarrier), zeroes and later writes its own gS slice, and keeps a private gC copy; the only CTA-wide
 // synchronisation is one early barrier after C is staged.  The last warp to finish folds the gC
 // copies and the NLL partials and writes them out.
-// Shared memory (floats): Ssm[TP][RP] | gSsm[TP][RP] | Csm[K+1][RP] | gCw[W][K+1][RP]; band row K is a
+// Shared memory (floats): ring[W][4][32][4] | Ssm[TP][RP] | gSsm[TP][RP] | Csm[K+1][RP] | gCw[W][K+1][RP]; band row K is a
 // dummy that absorbs the flush of a lane that owns no band.
 
 // ---- packed fp32x2 arithmetic (FFMA2/FMUL2/FADD2, sm_100) --------------------------------------
@@ -77,6 +77,18 @@ __device__ __forceinline__ uint4 ldg_u4(const uint4* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS, L2 only) and its in-order group accounting
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128_u4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // lane-stream word (qmc_obs_build_lanes): bit 31 = level & 1, bits 24..30 = level >> 1, bits 15..23 = band,
@@ -89,7 +101,8 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   extern __shared__ __align__(16) float smem[];
   const int W = prm.tile_warps, K = prm.K;
   const int TP = prm.sub_pixels * W;
-  float* Ssm = smem;
+  float* ring = smem;  // [W][LANES_DEPTH][32 lanes][4 words], first: 16-byte aligned for any rank
+  float* Ssm = ring + (size_t)W * LANES_DEPTH * 32 * 4;
   float* gSsm = Ssm + (size_t)TP * RP;
   float* Csm = gSsm + (GRAD ? (size_t)TP * RP : 0);
   float* gCw = Csm + (size_t)(K + 1) * RP;
@@ -127,9 +140,16 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   const int64_t stream = (int64_t)b * prm.n_sub + (int64_t)tile * W + warp;
   const uint4* gp = reinterpret_cast<const uint4*>(
                         prm.words + (prm.stream_stride > 0 ? stream * prm.stream_stride : prm.stream_off[stream])) + lane;
-  // four groups of register look-ahead (the stream is read once, straight from DRAM); every stream has
-  // room for at least four groups, so the first loads need not know its length
-  uint4 w0 = ldg_u4(gp), w1 = ldg_u4(gp + 32), w2 = ldg_u4(gp + 64), w3 = ldg_u4(gp + 96);
+  // LANES_DEPTH groups of look-ahead through a per-lane ring in shared memory, filled by asynchronous
+  // copies (the stream is read once, straight from DRAM; cp.async groups complete in order, which plain
+  // loads sharing a scoreboard do not guarantee).  Every stream has room for at least LANES_DEPTH groups, so
+  // the first copies need not know its length.
+  const uint32_t ring_a = smem_u32(ring) + (uint32_t)((warp * LANES_DEPTH) * 32 + lane) * 16u;
+#pragma unroll
+  for (int d = 0; d < LANES_DEPTH; ++d) {
+    cp_async16(ring_a + d * 512, gp + d * 32);
+    cp_async_commit();
+  }
   const int nrows_v = __ldg(prm.nrows + stream);
   const int cn = RP * (K + 1);
   float cv0 = 0.0f, cv1 = 0.0f;  // C staged as [k][r]: element i -> (r = i / (K+1), k = i % (K+1))
@@ -351,20 +371,18 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     }
   };
 
-  // unrolled by the look-ahead depth so that every buffer keeps its registers (a rotating copy would
-  // wait for the newest load every iteration)
-#define QMC_LANES_STAGE(WX)                                   \
-  if (grp >= ngroups) break;                                  \
-  group(WX);                                                  \
-  WX = ldg_u4(gp + (size_t)min(grp + 4, last) * 32);          \
-  ++grp;
-  for (int grp = 0;;) {
-    QMC_LANES_STAGE(w0)
-    QMC_LANES_STAGE(w1)
-    QMC_LANES_STAGE(w2)
-    QMC_LANES_STAGE(w3)
+  int slot = 0;
+#pragma unroll 1
+  for (int grp = 0; grp < ngroups; ++grp) {
+    cp_async_wait<LANES_DEPTH - 1>();  // group grp has landed (this lane reads only what it copied itself)
+    const uint32_t sa = ring_a + slot * 512;
+    const uint4 wv = lds128_u4(sa);
+    cp_async16(sa, gp + (size_t)min(grp + LANES_DEPTH, last) * 32);  // refill the slot just read
+    cp_async_commit();
+    slot = (slot + 1) & (LANES_DEPTH - 1);
+    group(wv);
   }
-#undef QMC_LANES_STAGE
+  cp_async_wait<0>();
   switch_band((uint32_t)K << LW_BAND_SHIFT);  // flush the last band
 
   // ---- epilogue: own gS slice out, then the last warp folds gC and the NLL -----------------------

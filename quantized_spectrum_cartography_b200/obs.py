@@ -20,7 +20,7 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def plan_tiles(IJ: int, K: int, R: int, tile_warps: int = 8, smem_budget: int = 100 * 1024, lanes: bool = False):
+def plan_tiles(IJ: int, K: int, R: int, tile_warps: int = 8, smem_budget: int = 110 * 1024, lanes: bool = False):
     """Choose the pixel sub-tile size for the shared-memory (tiled) kernel.
 
     Returns (n_sub, sub_pixels, tile_warps).  A tile is ``tile_warps`` sub-tiles; its S and gS
@@ -34,7 +34,7 @@ def plan_tiles(IJ: int, K: int, R: int, tile_warps: int = 8, smem_budget: int = 
         while tile_warps > 1 and (1 + tile_warps) * (K + 1) * RP * 4 > smem_budget // 2:
             tile_warps //= 2
         wc = tile_warps
-        fixed = (1 + wc) * (K + 1) * RP * 4 + 2 * 32 * RP * 4 + 16
+        fixed = (1 + wc) * (K + 1) * RP * 4 + tile_warps * 4 * 512 + 16      # C, gC copies, stream rings
     else:
         wc = tile_warps if tile_warps * K * RP * 4 <= 32 * 1024 else 1     # private gC copies (qmc_gather.cu)
         fixed = (1 + wc) * K * RP * 4 + tile_warps * (K + 2) * 4 + tile_warps * 32 * RP * 4 + 16
