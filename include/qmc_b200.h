@@ -142,7 +142,9 @@ QMC_API int qmc_obs_fill(const void* y_dev, int y_is_int64, const float* wx_dev,
  * are used as scratch and come back permuted inside their rows.  stream_off_dev: caller-chosen
  * capacities in words (multiples of 128; 32 * (1.3 * n * G / K + 4 * G + 8) words, G = ceil(K/32), for a stream of n
  * entries is ample); nrows_out_dev receives the steps actually used; *overflow_dev is set to 1 if a
- * stream did not fit its capacity.  K <= 256, levels <= 254, tile_warps * sub_pixels + 32 <= 32768. */
+ * stream did not fit its capacity.  Every stream must have room for at least 16 steps (the kernel loads
+ * its first four groups before it knows the length).  K <= 256, levels <= 254,
+ * tile_warps * sub_pixels + 32 <= 32768. */
 QMC_API int qmc_obs_build_lanes(int32_t* idx_rows_dev, uint8_t* lvl_rows_dev, const int64_t* row_off_dev,
                         int B, int K, int IJ, int n_sub, int sub_pixels, int tile_warps,
                         const int64_t* stream_off_dev, uint32_t* words_out_dev, int32_t* nrows_out_dev,
@@ -225,6 +227,27 @@ QMC_API int qmc_get_tensor(const float* S_dev, const float* C_dev, int B, int IJ
  * quantization_model_log.py:104-111) without materialising X_hat.  out_dev: 2*B doubles. */
 QMC_API int qmc_nmse_terms(const float* S_dev, const float* C_dev, const float* X_ref_dev, int B, int IJ,
                    int K, int R, int log_domain, float offset, double* out_dev, void* stream);
+
+/* ---- solver step: what the notebook does with torch.optim.Adam around the path ---- */
+
+/* out[b] = sum of squares of map b of x (n_per_map contiguous floats per map): ||.||_F^2 of
+ * torch.norm(., 'fro'), qmc/qmc.ipynb c1:151,209. */
+QMC_API int qmc_sumsq_per_map(const float* x_dev, int B, int64_t n_per_map, double* out_dev, void* stream);
+
+/* One fused factor update per map b, elementwise over n_per_map contiguous floats:
+ *   g' = g + lam * p / sqrt(sumsq_in[b])        gradient of lam*||p||_F (0 where the norm is 0)
+ *   Adam(lr, beta1, beta2, eps) moments m, v and step number t, torch.optim.Adam arithmetic
+ *   p  = max(p - step, 0) if project             the notebook's `X[X < 0] = 0`
+ *   sumsq_out[b] = sum p^2 after the update      (NULL to skip; sumsq_in may be NULL when lam == 0)
+ * t = step + (*step_dev if step_dev else 0), t >= 1.  Replaces opt.zero_grad / cost.backward's norm
+ * term / opt.step / projection of qmc/qmc.ipynb c1:126-128,151-157,209-212. */
+QMC_API int qmc_adam_frob_project(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, int B,
+                          int64_t n_per_map, const double* sumsq_in_dev, double* sumsq_out_dev, float lr,
+                          float beta1, float beta2, float eps, float lam, int project, int step,
+                          const int32_t* step_dev, void* stream);
+
+/* *counter_dev += add on the stream (the step counter of a CUDA-graph-captured solver iteration). */
+QMC_API int qmc_counter_add(int32_t* counter_dev, int add, void* stream);
 
 #ifdef __cplusplus
 }

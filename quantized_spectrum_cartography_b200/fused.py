@@ -77,9 +77,10 @@ def _pixel_major(S3: torch.Tensor) -> bool:
 
 
 def nll_fwd_bwd(S3: torch.Tensor, C3: torch.Tensor, obs: ObsSet, lik: Likelihood, *, algo: int = _lib.QMC_ALGO_AUTO,
-                want_grad: bool = True):
+                want_grad: bool = True, out=None):
     """Raw call: S3 [B,R,IJ] fp32 CUDA (emitter-major contiguous, or pixel-major storage viewed
-    as [B,R,IJ]), C3 [B,R,K].  Returns (nll fp64 [B], gS like S3 or None, gC [B,R,K] or None)."""
+    as [B,R,IJ]), C3 [B,R,K].  Returns (nll fp64 [B], gS like S3 or None, gC [B,R,K] or None).
+    ``out=(nll, gS, gC)`` reuses buffers of those shapes, dtypes and strides."""
     if not (S3.is_cuda and C3.is_cuda):
         raise ValueError("nll_fwd_bwd needs CUDA tensors: there is no CPU path")
     if S3.dtype != torch.float32 or C3.dtype != torch.float32:
@@ -99,9 +100,14 @@ def nll_fwd_bwd(S3: torch.Tensor, C3: torch.Tensor, obs: ObsSet, lik: Likelihood
     C3 = C3.contiguous()
     lik = _with_flags(lik, not want_grad)
     with torch.cuda.device(S3.device):
-        nll = torch.empty(B, dtype=torch.float64, device=S3.device)
-        gS = torch.empty_strided(S3.shape, S3.stride(), dtype=torch.float32, device=S3.device) if want_grad else None
-        gC = torch.empty_like(C3) if want_grad else None
+        if out is not None:
+            nll, gS, gC = out
+            if want_grad and (gS.stride() != S3.stride() or not gC.is_contiguous()):
+                raise ValueError("out buffers must have the strides of S3 (gS) and be contiguous (gC)")
+        else:
+            nll = torch.empty(B, dtype=torch.float64, device=S3.device)
+            gS = torch.empty_strided(S3.shape, S3.stride(), dtype=torch.float32, device=S3.device) if want_grad else None
+            gC = torch.empty_like(C3) if want_grad else None
         view = obs.view()
         check(lib.qmc_nll_fwd_bwd_gather(
             S3.data_ptr(), S3.stride(0), S3.stride(1), S3.stride(2), C3.data_ptr(), C.byref(view), C.byref(lik),

@@ -147,6 +147,98 @@ def solve_lowrank(S0: torch.Tensor, C0: torch.Tensor, nll_fn: Callable[[torch.Te
     return res
 
 
+def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: SolverConfig = SolverConfig(),
+                        nmse_fn: Optional[Callable] = None, betas=(0.9, 0.999), eps: float = 1e-8) -> SolverResult:
+    """The iteration of :func:`solve_lowrank` without autograd and without torch.optim: every step is
+    one fused likelihood evaluation (``fused.nll_fwd_bwd``) followed by one fused update
+    (``qmc_adam_frob_project``: regulariser gradient, Adam, projection, next squared norm) -- four
+    kernels per alternating iteration instead of ~60.  Same arithmetic as the torch path to fp32
+    rounding (``tests/test_gpu_parity.py::test_fused_solver_matches_torch_solver``).
+
+    ``S0`` may be emitter-major contiguous or pixel-major storage viewed as ``[B,R,IJ]``; its layout
+    is kept.  ``cfg.cuda_graph`` captures one iteration (the Adam step number then lives on the device)."""
+    import ctypes as C
+    from . import _lib
+    from ._lib import check, lib
+    from .fused import nll_fwd_bwd
+    if not S0.is_cuda:
+        raise ValueError("solve_lowrank_fused needs CUDA tensors: there is no CPU path")
+    dev = S0.device
+    S = torch.empty_strided(S0.shape, S0.stride(), dtype=torch.float32, device=dev)
+    S.copy_(S0.detach())
+    Cf = C0.detach().to(torch.float32).contiguous().clone()
+    B, R, IJ = S.shape
+    K = Cf.shape[2]
+    nS, nC = R * IJ, R * K
+    dense_s = S.is_contiguous() or (S.stride(1) == 1 and S.stride(2) == R and S.stride(0) == nS)
+    if not dense_s:
+        raise ValueError("S must be a dense [B,R,IJ] tensor (emitter-major or pixel-major storage)")
+    mS, vS = torch.zeros_like(S), torch.zeros_like(S)
+    mC, vC = torch.zeros_like(Cf), torch.zeros_like(Cf)
+    if mS.stride() != S.stride():
+        raise RuntimeError("moment buffers did not keep the layout of S")
+    gS = torch.empty_strided(S.shape, S.stride(), dtype=torch.float32, device=dev)
+    gC = torch.empty_like(Cf)
+    nll = torch.empty(B, dtype=torch.float64, device=dev)
+    ssS, ssS_next = (torch.empty(B, dtype=torch.float64, device=dev) for _ in range(2))   # ||S_b||_F^2
+    ssC, ssC_next = (torch.empty(B, dtype=torch.float64, device=dev) for _ in range(2))
+    ctr = torch.zeros(2, dtype=torch.int32, device=dev)          # Adam steps taken on C, on S
+    ctr_c, ctr_s = ctr.data_ptr(), ctr.data_ptr() + 4
+    res = SolverResult(S, Cf)
+
+    def stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def update(p, g, m, v, n, ss, ss_next, lr, lam, project, ctr_ptr):
+        check(lib.qmc_adam_frob_project(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), B, n,
+                                        ss.data_ptr(), ss_next.data_ptr(), lr, betas[0], betas[1], eps, lam,
+                                        int(project), 1, ctr_ptr, stream()))
+        check(lib.qmc_counter_add(ctr_ptr, 1, stream()))
+        ss.copy_(ss_next)
+
+    def iteration():
+        for j in range(cfg.c_inner):
+            nll_fwd_bwd(S, Cf, obs, lik, out=(nll, gS, gC))
+            update(Cf, gC, mC, vC, nC, ssC, ssC_next, cfg.lr_c, cfg.lam_c, cfg.project_c and j == cfg.c_inner - 1, ctr_c)
+        cost = None
+        for j in range(cfg.s_inner):
+            nll_fwd_bwd(S, Cf, obs, lik, out=(nll, gS, gC))
+            cost = nll.to(torch.float32) + cfg.lam_s * ssS.sqrt().to(torch.float32)
+            update(S, gS, mS, vS, nS, ssS, ssS_next, cfg.lr_s, cfg.lam_s, cfg.project_s and j == cfg.s_inner - 1, ctr_s)
+        return cost
+
+    with torch.cuda.device(dev):
+        check(lib.qmc_sumsq_per_map(S.data_ptr(), B, nS, ssS.data_ptr(), stream()))
+        check(lib.qmc_sumsq_per_map(Cf.data_ptr(), B, nC, ssC.data_ptr(), stream()))
+        graph = None
+        if cfg.cuda_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):      # warm-up launch outside the capture (kernel attributes)
+                nll_fwd_bwd(S, Cf, obs, lik, out=(nll, gS, gC))
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_cost = iteration()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for it in range(cfg.iters):
+            if graph is not None:
+                graph.replay()
+                cost = static_cost
+            else:
+                cost = iteration()
+            if cfg.track_every and (it % cfg.track_every == 0 or it == cfg.iters - 1):
+                res.cost.append(cost.detach().clone())
+                if nmse_fn is not None:
+                    res.nmse.append(nmse_fn(S, Cf))
+        torch.cuda.synchronize()
+        res.seconds = time.perf_counter() - t0
+    res.iterations = cfg.iters
+    res.S, res.C = S, Cf
+    return res
+
+
 def cuda_nll_fn(obs, lik):
     """The product backend: fused CUDA likelihood of a batch of maps."""
     from .fused import qmc_nll_batched
@@ -211,13 +303,17 @@ def main(argv=None):
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--graph", action="store_true", help="replay one captured iteration (CUDA graph)")
+    ap.add_argument("--torch-optim", action="store_true", help="autograd + torch.optim.Adam instead of the fused update kernel")
     args = ap.parse_args(argv)
     dev = torch.device("cuda", torch.cuda.current_device())
     pb = synth_problem(args.config, args.maps, dev, args.seed)
     maps = pb["maps"]
     cfg = SolverConfig(iters=args.iters, lam_c=1.0, lam_s=1.0, track_every=max(1, args.iters // 10), cuda_graph=args.graph)
-    res = solve_lowrank(0.7 * maps.S_true, 0.9 * maps.C_true, cuda_nll_fn(pb["obs"], pb["lik"]), cfg,
-                        cuda_nmse_fn(pb["T"]))
+    if args.torch_optim:
+        res = solve_lowrank(0.7 * maps.S_true, 0.9 * maps.C_true, cuda_nll_fn(pb["obs"], pb["lik"]), cfg,
+                            cuda_nmse_fn(pb["T"]))
+    else:
+        res = solve_lowrank_fused(0.7 * maps.S_true, 0.9 * maps.C_true, pb["obs"], pb["lik"], cfg, cuda_nmse_fn(pb["T"]))
     for i, (c, n) in enumerate(zip(res.cost, res.nmse)):
         print(f"track {i}: cost[0]={c[0].item():.4f} nmse[0]={n.reshape(-1)[0].item():.5f}")
     print(f"{res.iterations} iterations x {args.maps} maps in {res.seconds:.3f} s -> "

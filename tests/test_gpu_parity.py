@@ -511,6 +511,35 @@ def test_cuda_graph_solver_matches_eager(q):
         np.testing.assert_allclose(nb.cpu().numpy(), na.cpu().numpy(), rtol=1e-4)
 
 
+@pytest.mark.parametrize("K,tiled,pixel_major,graph", [(16, True, False, False), (64, True, True, False),
+                                                       (64, True, True, True), (16, False, False, False)])
+def test_fused_solver_matches_torch_solver(q, K, tiled, pixel_major, graph):
+    """The autograd-free solver (fused evaluation + qmc_adam_frob_project) walks the same trajectory as
+    autograd + torch.optim.Adam + torch.norm + clamp_ on the same start point."""
+    from quantized_spectrum_cartography_b200 import qmc
+    B, I, J, R = 5, 20, 21, 4
+    S, C, Y, Wx, bb, sigma, off = _random_instance(B, I, J, K, R, 0.3, 2, seed=78)
+    lik = q.make_likelihood(bb, sigma)
+    obs = q.make_obs(Y.cuda(), Wx.cuda(), K, "cuda", B=B, R=R, tiled=tiled, tile_warps=4)
+    T = torch.einsum("brp,brk->bkp", S, C).cuda()
+    S0 = 0.8 * S.cuda()
+    if pixel_major:
+        S0 = S0.transpose(1, 2).contiguous().transpose(1, 2)
+    cfg = qmc.SolverConfig(iters=12, lr_c=0.005, lr_s=0.001, lam_c=3.0, lam_s=2.0, track_every=4)
+    a = qmc.solve_lowrank(S0, 1.1 * C.cuda(), qmc.cuda_nll_fn(obs, lik), cfg, qmc.cuda_nmse_fn(T))
+    cfg_f = qmc.SolverConfig(iters=12, lr_c=0.005, lr_s=0.001, lam_c=3.0, lam_s=2.0, track_every=4, cuda_graph=graph)
+    b = qmc.solve_lowrank_fused(S0, 1.1 * C.cuda(), obs, lik, cfg_f, qmc.cuda_nmse_fn(T))
+    assert b.S.stride() == S0.stride()
+    assert rel_err(b.S.cpu().numpy(), a.S.cpu().numpy()) < 2e-5
+    assert rel_err(b.C.cpu().numpy(), a.C.cpu().numpy()) < 2e-5
+    assert len(a.cost) == len(b.cost) == 4
+    for ca, cb in zip(a.cost, b.cost):
+        np.testing.assert_allclose(cb.cpu().numpy(), ca.cpu().numpy(), rtol=2e-5)
+    for na, nb in zip(a.nmse, b.nmse):
+        np.testing.assert_allclose(nb.cpu().numpy().reshape(-1), na.cpu().numpy().reshape(-1), rtol=1e-4)
+    assert (b.S >= 0).all() and (b.C >= 0).all()
+
+
 @pytest.mark.parametrize("B,I,J,K,R,levels,log_domain,f,tw,n_tiles", [
     (5, 51, 51, 64, 4, 2, False, 0.10, 8, 1),      # cfg1/cfg3 geometry
     (3, 30, 31, 40, 3, 4, True, 0.30, 4, 2),       # K not a multiple of 32, two tiles per map, padded rank
