@@ -55,7 +55,12 @@ enum {
                                   0.5*(1+erf(zl)) in fp32 (quantization_model.py:38,61): loses the
                                   tails exactly where the reference does.  Default is the numerically
                                   stable log-difference of scaled complementary error functions. */
-  QMC_FORWARD_ONLY = 1u << 2   /* NLL only, no gradients (random-restart search, qmc.ipynb c1:168-197) */
+  QMC_FORWARD_ONLY = 1u << 2,  /* NLL only, no gradients (random-restart search, qmc.ipynb c1:168-197) */
+  QMC_SKIP_GS = 1u << 3,       /* the caller does not need gS (the C-step of the alternating solver, qmc.ipynb
+                                  c1:140-154: S is detached): the lane-stream kernel skips its shared-memory
+                                  updates and the write; other kernels ignore the flag.  gS_out may then be
+                                  NULL for the lane-stream kernel only. */
+  QMC_SKIP_GC = 1u << 4        /* likewise for gC (the S-step, c1:199-212) */
 };
 
 /*

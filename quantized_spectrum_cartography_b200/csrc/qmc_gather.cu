@@ -50,7 +50,10 @@ extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, in
   QMC_REQUIRE(obs->n_sub > 0 && obs->sub_pixels > 0 && (int64_t)obs->n_sub * obs->sub_pixels >= IJ,
               "sub-tiles (%d x %d) do not cover IJ=%d", obs->n_sub, obs->sub_pixels, IJ);
   const bool grad = !(lik->flags & QMC_FORWARD_ONLY);
-  QMC_REQUIRE(!grad || (gS_out_dev && gC_out_dev), "gradient outputs are NULL without QMC_FORWARD_ONLY");
+  const bool lanes_set = obs->words_dev != nullptr;
+  const bool want_gs = grad && !(lanes_set && (lik->flags & QMC_SKIP_GS));
+  const bool want_gc = grad && !(lanes_set && (lik->flags & QMC_SKIP_GC));
+  QMC_REQUIRE((!want_gs || gS_out_dev) && (!want_gc || gC_out_dev), "a requested gradient output is NULL");
   cudaStream_t st = (cudaStream_t)stream;
 
   GatherParams prm;
@@ -59,6 +62,7 @@ extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, in
   prm.words = obs->words_dev; prm.stream_off = obs->stream_off_dev; prm.nrows = obs->nrows_dev;
   prm.stream_stride = lanes ? obs->stream_stride : 0;
   prm.lookahead = 0;
+  prm.want_gs = want_gs; prm.want_gc = want_gc;
   prm.nll = nll_out_dev; prm.gS = gS_out_dev; prm.gC = gC_out_dev;
   prm.n_sub = obs->n_sub; prm.sub_pixels = obs->sub_pixels;
   prm.B = B; prm.IJ = IJ; prm.K = K; prm.R = R;
@@ -140,7 +144,7 @@ extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, in
   const bool atomics_on_out = (algo == QMC_ALGO_FLAT) || prm.tiles_per_map > 1;
   if (atomics_on_out) {
     QMC_CUDA_CHECK(cudaMemsetAsync(nll_out_dev, 0, sizeof(double) * B, st));
-    if (grad) QMC_CUDA_CHECK(cudaMemsetAsync(gC_out_dev, 0, sizeof(float) * (size_t)B * R * K, st));
+    if (want_gc) QMC_CUDA_CHECK(cudaMemsetAsync(gC_out_dev, 0, sizeof(float) * (size_t)B * R * K, st));
   }
   if (grad && algo == QMC_ALGO_FLAT) {
     // gS may be strided: zero the dense extent it spans only when it is compact

@@ -20,6 +20,7 @@ struct GatherParams {
   const int32_t* nrows;       // lane-stream layout: steps per stream (multiple of 4)
   int64_t stream_stride;      // lane-stream layout: > 0 = uniform stream capacity in words (no table look-up)
   int lookahead;              // lanes kernel: CTAs resident on the device (prefetch distance in CTAs)
+  int want_gs, want_gc;       // lanes kernel: which gradients the caller needs (QMC_SKIP_GS / QMC_SKIP_GC)
   double* nll;
   float* gS;
   float* gC;

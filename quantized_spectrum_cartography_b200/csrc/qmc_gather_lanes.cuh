@@ -118,9 +118,10 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   const int nthr = blockDim.x;
   const float* __restrict__ Sb = prm.S + b * prm.sB;
   const float* __restrict__ Cb = prm.C + (int64_t)b * prm.R * K;
-  float* gSb = GRAD ? prm.gS + b * prm.sB : nullptr;
+  const bool do_gs = GRAD && prm.want_gs, do_gc = GRAD && prm.want_gc;  // uniform over the grid
+  float* gSb = do_gs ? prm.gS + b * prm.sB : nullptr;
   const bool bulk = (prm.sR == 1 && prm.sP == RP && prm.R == RP && (RP % 4) == 0 &&
-                     ((reinterpret_cast<uintptr_t>(Sb) | (GRAD ? reinterpret_cast<uintptr_t>(gSb) : 0)) & 15) == 0);
+                     ((reinterpret_cast<uintptr_t>(Sb) | (do_gs ? reinterpret_cast<uintptr_t>(gSb) : 0)) & 15) == 0);
   // this warp's pixel slice of the tile
   const int sl0 = min(warp * prm.sub_pixels, np);
   const int sln = min((warp + 1) * prm.sub_pixels, np) - sl0;
@@ -187,11 +188,11 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   if (GRAD) {
     if (RP % 4 == 0) {
       float4* z = reinterpret_cast<float4*>(gSw);
-      for (int i = lane; i < sln * (RP / 4); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = lane; i < (do_gs ? sln * (RP / 4) : 0); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       float4* zc = reinterpret_cast<float4*>(gCw + (size_t)warp * (K + 1) * RP);
       for (int i = lane; i < (K + 1) * (RP / 4); i += 32) zc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
-      for (int i = lane; i < sln * RP; i += 32) gSw[i] = 0.0f;
+      for (int i = lane; i < (do_gs ? sln * RP : 0); i += 32) gSw[i] = 0.0f;
       float* zc = gCw + (size_t)warp * (K + 1) * RP;
       for (int i = lane; i < (K + 1) * RP; i += 32) zc[i] = 0.0f;
     }
@@ -342,6 +343,22 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     }
     if (GRAD) {
 #pragma unroll
+      for (int j = 0; j < 4; ++j) {  // gC: registers only
+        if (RP % 2 == 0) {
+          const f2 g2 = bc2(g[j]);
+#pragma unroll
+          for (int r = 0; r < RP; r += 2) {
+            const f2 a = fma2(g2, mk2(sv[j][r], sv[j][r + 1]), mk2(acc[r], acc[r + 1]));
+            un2(a, acc[r], acc[r + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < RP; ++r) acc[r] = fmaf(g[j], sv[j][r], acc[r]);
+        }
+      }
+    }
+    if (do_gs) {
+#pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t rs = srow[j] + gS_delta;
         if (RP % 4 == 0) {
@@ -355,16 +372,9 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
             un2(bq, v.z, v.w);
             sts128_if(rs + r * 4, v, ok[j]);
           }
-#pragma unroll
-          for (int r = 0; r < RP; r += 2) {
-            const f2 a = fma2(g2, mk2(sv[j][r], sv[j][r + 1]), mk2(acc[r], acc[r + 1]));
-            un2(a, acc[r], acc[r + 1]);
-          }
         } else {
 #pragma unroll
           for (int r = 0; r < RP; ++r) sts32_if(rs + r * 4, fmaf(g[j], c[r], lds32(rs + r * 4)), ok[j]);
-#pragma unroll
-          for (int r = 0; r < RP; ++r) acc[r] = fmaf(g[j], sv[j][r], acc[r]);
         }
       }
       __syncwarp();  // steps are applied in program order by the converged warp: a later step may touch the same pixel from another lane
@@ -393,7 +403,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   }
   const double wsumv = warp_sum((double)nll_part);
   if (lane == 0) wsum[warp] = wsumv;
-  if (GRAD && sln > 0) {
+  if (do_gs && sln > 0) {
     if (bulk) {
       fence_async_smem();  // generic-proxy writes to the slice -> visible to the bulk-copy engine
       __syncwarp();
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       if (prm.tiles_per_map == 1) prm.nll[b] = tot;
       else atomicAdd(prm.nll + b, tot);
     }
-    if (GRAD) {
+    if (do_gc) {
       float* gCb = prm.gC + (int64_t)b * prm.R * K;
 #pragma unroll
       for (int r = 0; r < RP; ++r) {
@@ -433,7 +443,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       }
     }
   }
-  if (GRAD && bulk && sln > 0 && lane == 0) bulk_wait_all();  // the slice must stay alive until the engine has read it
+  if (do_gs && bulk && sln > 0 && lane == 0) bulk_wait_all();  // the slice must stay alive until the engine has read it
 }
 
 template <int RP, int EPI, bool LOGD, bool GRAD>

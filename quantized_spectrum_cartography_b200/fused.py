@@ -77,10 +77,12 @@ def _pixel_major(S3: torch.Tensor) -> bool:
 
 
 def nll_fwd_bwd(S3: torch.Tensor, C3: torch.Tensor, obs: ObsSet, lik: Likelihood, *, algo: int = _lib.QMC_ALGO_AUTO,
-                want_grad: bool = True, out=None):
+                want_grad: bool = True, out=None, skip_gs: bool = False, skip_gc: bool = False):
     """Raw call: S3 [B,R,IJ] fp32 CUDA (emitter-major contiguous, or pixel-major storage viewed
     as [B,R,IJ]), C3 [B,R,K].  Returns (nll fp64 [B], gS like S3 or None, gC [B,R,K] or None).
-    ``out=(nll, gS, gC)`` reuses buffers of those shapes, dtypes and strides."""
+    ``out=(nll, gS, gC)`` reuses buffers of those shapes, dtypes and strides.  ``skip_gs`` / ``skip_gc``
+    tell the lane-stream kernel that one gradient is not needed (its buffer is then left untouched);
+    the other kernels compute both regardless."""
     if not (S3.is_cuda and C3.is_cuda):
         raise ValueError("nll_fwd_bwd needs CUDA tensors: there is no CPU path")
     if S3.dtype != torch.float32 or C3.dtype != torch.float32:
@@ -99,6 +101,8 @@ def nll_fwd_bwd(S3: torch.Tensor, C3: torch.Tensor, obs: ObsSet, lik: Likelihood
         S3 = S3.contiguous()
     C3 = C3.contiguous()
     lik = _with_flags(lik, not want_grad)
+    if want_grad and obs.lanes:
+        lik.flags |= (_lib.QMC_SKIP_GS if skip_gs else 0) | (_lib.QMC_SKIP_GC if skip_gc else 0)
     with torch.cuda.device(S3.device):
         if out is not None:
             nll, gS, gC = out

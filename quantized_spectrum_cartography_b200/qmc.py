@@ -198,11 +198,11 @@ def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: Solve
 
     def iteration():
         for j in range(cfg.c_inner):
-            nll_fwd_bwd(S, Cf, obs, lik, out=(nll, gS, gC))
+            nll_fwd_bwd(S, Cf, obs, lik, out=(nll, gS, gC), skip_gs=True)
             update(Cf, gC, mC, vC, nC, ssC, ssC_next, cfg.lr_c, cfg.lam_c, cfg.project_c and j == cfg.c_inner - 1, ctr_c)
         cost = None
         for j in range(cfg.s_inner):
-            nll_fwd_bwd(S, Cf, obs, lik, out=(nll, gS, gC))
+            nll_fwd_bwd(S, Cf, obs, lik, out=(nll, gS, gC), skip_gc=True)
             cost = nll.to(torch.float32) + cfg.lam_s * ssS.sqrt().to(torch.float32)
             update(S, gS, mS, vS, nS, ssS, ssS_next, cfg.lr_s, cfg.lam_s, cfg.project_s and j == cfg.s_inner - 1, ctr_s)
         return cost

@@ -618,3 +618,11 @@ def test_lane_stream_builder_and_kernel(q, B, I, J, K, R, levels, log_domain, f,
     assert torch.equal(gS_p.contiguous(), gS) or rel_err(gS_p.cpu().numpy(), gS.cpu().numpy()) < 1e-6
     nll_o, _, _ = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik, want_grad=False)
     np.testing.assert_allclose(nll_o.cpu().numpy(), nll.cpu().numpy(), rtol=1e-12)
+    # one gradient only (the C-step / S-step of the solver): the other buffer is left alone
+    mark = torch.full_like(gS, 7.0), torch.full_like(gC, 7.0)
+    nll_c, gS_c, gC_c = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik, out=(torch.empty_like(nll), mark[0], gC.clone().zero_()), skip_gs=True)
+    assert torch.equal(gS_c, torch.full_like(gS, 7.0)) and rel_err(gC_c.cpu().numpy(), gC.cpu().numpy()) < 1e-6
+    np.testing.assert_allclose(nll_c.cpu().numpy(), nll.cpu().numpy(), rtol=1e-12)
+    nll_s, gS_s, gC_s = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik, out=(torch.empty_like(nll), gS.clone().zero_(), mark[1]), skip_gc=True)
+    assert torch.equal(gC_s, torch.full_like(gC, 7.0)) and rel_err(gS_s.cpu().numpy(), gS.cpu().numpy()) < 1e-6
+    np.testing.assert_allclose(nll_s.cpu().numpy(), nll.cpu().numpy(), rtol=1e-12)
