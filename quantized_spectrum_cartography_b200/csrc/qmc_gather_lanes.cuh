@@ -180,10 +180,27 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     }
   }
   if (!bulk) {
+    // emitter-major storage (the reference's): coalesced row reads transposed into [p][r]; the loads of
+    // SU pixels per lane are all in flight before the first store waits for one
+    constexpr int SU = RP <= 8 ? 4 : 1;
+    for (int i0 = 0; i0 < sln; i0 += 32 * SU) {
+      float tmp[SU][RP];
 #pragma unroll
-    for (int r = 0; r < RP; ++r)
-      for (int pl = lane; pl < sln; pl += 32)
-        Sw[pl * RP + r] = (r < prm.R) ? __ldg(Sb + r * prm.sR + (int64_t)(p0 + sl0 + pl) * prm.sP) : 0.0f;
+      for (int u = 0; u < SU; ++u) {
+        const int pl = i0 + u * 32 + lane;
+#pragma unroll
+        for (int r = 0; r < RP; ++r)
+          tmp[u][r] = (pl < sln && r < prm.R) ? __ldg(Sb + r * prm.sR + (int64_t)(p0 + sl0 + pl) * prm.sP) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        const int pl = i0 + u * 32 + lane;
+        if (pl < sln) {
+#pragma unroll
+          for (int r = 0; r < RP; ++r) Sw[pl * RP + r] = tmp[u][r];
+        }
+      }
+    }
   }
   if (GRAD) {
     if (RP % 4 == 0) {

@@ -155,8 +155,8 @@ def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: Solve
     kernels per alternating iteration instead of ~60.  Same arithmetic as the torch path to fp32
     rounding (``tests/test_gpu_parity.py::test_fused_solver_matches_torch_solver``).
 
-    ``S0`` may be emitter-major contiguous or pixel-major storage viewed as ``[B,R,IJ]``; its layout
-    is kept.  ``cfg.cuda_graph`` captures one iteration (the Adam step number then lives on the device)."""
+    ``S0`` may be emitter-major contiguous or pixel-major storage viewed as ``[B,R,IJ]``; the result
+    comes back in the same layout (internally S lives pixel-major when R is a multiple of 4).  ``cfg.cuda_graph`` captures one iteration (the Adam step number then lives on the device)."""
     import ctypes as C
     from . import _lib
     from ._lib import check, lib
@@ -164,10 +164,15 @@ def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: Solve
     if not S0.is_cuda:
         raise ValueError("solve_lowrank_fused needs CUDA tensors: there is no CPU path")
     dev = S0.device
-    S = torch.empty_strided(S0.shape, S0.stride(), dtype=torch.float32, device=dev)
+    B, R, IJ = S0.shape
+    if R % 4 == 0:
+        # pixel-major storage [B][IJ][R] viewed as [B,R,IJ]: the kernels stage and write whole tiles with
+        # TMA bulk copies; the caller gets S back in the layout it passed
+        S = torch.empty(B, IJ, R, dtype=torch.float32, device=dev).transpose(1, 2)
+    else:
+        S = torch.empty_strided(S0.shape, S0.stride(), dtype=torch.float32, device=dev)
     S.copy_(S0.detach())
     Cf = C0.detach().to(torch.float32).contiguous().clone()
-    B, R, IJ = S.shape
     K = Cf.shape[2]
     nS, nC = R * IJ, R * K
     dense_s = S.is_contiguous() or (S.stride(1) == 1 and S.stride(2) == R and S.stride(0) == nS)
@@ -235,7 +240,9 @@ def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: Solve
         torch.cuda.synchronize()
         res.seconds = time.perf_counter() - t0
     res.iterations = cfg.iters
-    res.S, res.C = S, Cf
+    S_out = torch.empty_strided(S0.shape, S0.stride(), dtype=torch.float32, device=dev)
+    S_out.copy_(S)
+    res.S, res.C = S_out, Cf
     return res
 
 
