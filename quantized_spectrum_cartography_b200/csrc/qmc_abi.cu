@@ -4,6 +4,8 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <mutex>
+
 #include "qmc_common.cuh"
 
 namespace qmc {
@@ -129,26 +131,68 @@ extern "C" int qmc_nmse_terms(const float* S_dev, const float* C_dev, const floa
   return QMC_OK;
 }
 
+// Host-buffer entry: the batch is cut into chunks of maps that flow through three internal streams, so
+// that the host->device copy of one chunk, the kernel of the previous one and the device->host copy of
+// the one before overlap (PCIe is full duplex; the kernel is a small fraction of either copy).
+namespace {
+struct HostPipe {
+  int dev = -1;
+  cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t start = nullptr;
+};
+HostPipe g_pipe;
+std::mutex g_pipe_mu;
+}  // namespace
+
 extern "C" int qmc_nll_fwd_bwd_gather_host(const float* S_host, const float* C_host, float* S_scratch_dev,
                                            float* C_scratch_dev, const qmc_obs_view_t* obs,
                                            const qmc_likelihood_t* lik, int B, int IJ, int K, int R, int algo,
                                            int tile_warps, double* nll_scratch_dev, float* gS_scratch_dev,
                                            float* gC_scratch_dev, double* nll_host, float* gS_host,
                                            float* gC_host, void* stream) {
-  QMC_REQUIRE(S_host && C_host && S_scratch_dev && C_scratch_dev && nll_scratch_dev && nll_host && lik, "null argument");
+  QMC_REQUIRE(S_host && C_host && S_scratch_dev && C_scratch_dev && nll_scratch_dev && nll_host && lik && obs, "null argument");
+  const bool grad = !(lik->flags & QMC_FORWARD_ONLY);
+  QMC_REQUIRE(!grad || (gS_host && gC_host && gS_scratch_dev && gC_scratch_dev), "null gradient buffers");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t nS = sizeof(float) * (size_t)B * R * IJ, nC = sizeof(float) * (size_t)B * R * K;
-  QMC_CUDA_CHECK(cudaMemcpyAsync(S_scratch_dev, S_host, nS, cudaMemcpyHostToDevice, st));
-  QMC_CUDA_CHECK(cudaMemcpyAsync(C_scratch_dev, C_host, nC, cudaMemcpyHostToDevice, st));
-  const int rc = qmc_nll_fwd_bwd_gather(S_scratch_dev, (int64_t)R * IJ, IJ, 1, C_scratch_dev, obs, lik, B, IJ, K, R,
-                                        algo, tile_warps, nll_scratch_dev, gS_scratch_dev, gC_scratch_dev, stream);
-  if (rc != QMC_OK) return rc;
-  QMC_CUDA_CHECK(cudaMemcpyAsync(nll_host, nll_scratch_dev, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-  if (!(lik->flags & QMC_FORWARD_ONLY)) {
-    QMC_REQUIRE(gS_host && gC_host, "null gradient host buffers");
-    QMC_CUDA_CHECK(cudaMemcpyAsync(gS_host, gS_scratch_dev, nS, cudaMemcpyDeviceToHost, st));
-    QMC_CUDA_CHECK(cudaMemcpyAsync(gC_host, gC_scratch_dev, nC, cudaMemcpyDeviceToHost, st));
+  std::lock_guard<std::mutex> lock(g_pipe_mu);
+  int dev = 0;
+  QMC_CUDA_CHECK(cudaGetDevice(&dev));
+  if (g_pipe.dev != dev) {
+    for (auto& x : g_pipe.s) {
+      if (x) cudaStreamDestroy(x);
+      QMC_CUDA_CHECK(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+    }
+    if (g_pipe.start) cudaEventDestroy(g_pipe.start);
+    QMC_CUDA_CHECK(cudaEventCreateWithFlags(&g_pipe.start, cudaEventDisableTiming));
+    g_pipe.dev = dev;
   }
-  QMC_CUDA_CHECK(cudaStreamSynchronize(st));
+  QMC_CUDA_CHECK(cudaEventRecord(g_pipe.start, st));
+  for (auto& x : g_pipe.s) QMC_CUDA_CHECK(cudaStreamWaitEvent(x, g_pipe.start, 0));
+
+  const int n_chunks = B >= 512 ? 8 : (B >= 64 ? 4 : 1);
+  const int per = (B + n_chunks - 1) / n_chunks;
+  const size_t sS = (size_t)R * IJ, sC = (size_t)R * K;
+  const int64_t streams_per_map = obs->n_sub, rows_per_map = (int64_t)obs->n_sub * K;
+  for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
+    const int nb = (B - b0) < per ? (B - b0) : per;
+    cudaStream_t cs = g_pipe.s[c % 3];
+    QMC_CUDA_CHECK(cudaMemcpyAsync(S_scratch_dev + b0 * sS, S_host + b0 * sS, sizeof(float) * nb * sS, cudaMemcpyHostToDevice, cs));
+    QMC_CUDA_CHECK(cudaMemcpyAsync(C_scratch_dev + b0 * sC, C_host + b0 * sC, sizeof(float) * nb * sC, cudaMemcpyHostToDevice, cs));
+    qmc_obs_view_t v = *obs;  // the observation arrays of maps b0.. (offsets stored in them are absolute)
+    if (v.row_off_dev) v.row_off_dev += b0 * rows_per_map;
+    if (v.nrows_dev) v.nrows_dev += b0 * streams_per_map;
+    if (v.words_dev && v.stream_stride > 0) v.words_dev += b0 * streams_per_map * v.stream_stride;
+    else if (v.stream_off_dev) v.stream_off_dev += b0 * streams_per_map;
+    const int rc = qmc_nll_fwd_bwd_gather(S_scratch_dev + b0 * sS, (int64_t)sS, IJ, 1, C_scratch_dev + b0 * sC, &v, lik, nb,
+                                          IJ, K, R, algo, tile_warps, nll_scratch_dev + b0,
+                                          grad ? gS_scratch_dev + b0 * sS : nullptr, grad ? gC_scratch_dev + b0 * sC : nullptr, cs);
+    if (rc != QMC_OK) return rc;
+    QMC_CUDA_CHECK(cudaMemcpyAsync(nll_host + b0, nll_scratch_dev + b0, sizeof(double) * nb, cudaMemcpyDeviceToHost, cs));
+    if (grad) {
+      QMC_CUDA_CHECK(cudaMemcpyAsync(gS_host + b0 * sS, gS_scratch_dev + b0 * sS, sizeof(float) * nb * sS, cudaMemcpyDeviceToHost, cs));
+      QMC_CUDA_CHECK(cudaMemcpyAsync(gC_host + b0 * sC, gC_scratch_dev + b0 * sC, sizeof(float) * nb * sC, cudaMemcpyDeviceToHost, cs));
+    }
+  }
+  for (auto& x : g_pipe.s) QMC_CUDA_CHECK(cudaStreamSynchronize(x));
   return QMC_OK;
 }

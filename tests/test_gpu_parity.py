@@ -348,6 +348,37 @@ def test_host_buffer_entry_point(q):
     assert rel_err(gCh.numpy(), want[2].cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("layout", ["flat", "tiled", "lanes"])
+def test_host_buffer_entry_point_pipelines_chunks(q, layout):
+    """B >= 64: the host entry cuts the batch into chunks on three streams; every observation layout must
+    address its chunk correctly (offsets stored in the arrays are absolute, the pointers move)."""
+    import ctypes as C_
+    from quantized_spectrum_cartography_b200 import _lib
+    B, I, J, K, R = 70, 9, 11, 32, 4
+    S, C, Y, Wx, bb, sigma, off = _random_instance(B, I, J, K, R, 0.3, 2, seed=10)
+    IJ = I * J
+    lik = q.make_likelihood(bb, sigma)
+    if layout == "flat":
+        obs = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, B)
+    else:
+        obs = q.make_obs(Y.cuda(), Wx.cuda(), K, "cuda", B=B, R=R, tiled=True, tile_warps=2, lanes=layout == "lanes")
+    want = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik)
+    Sh, Ch = S.contiguous().pin_memory(), C.contiguous().pin_memory()
+    gSh, gCh = torch.empty_like(Sh).pin_memory(), torch.empty_like(Ch).pin_memory()
+    nllh = torch.empty(B, dtype=torch.float64).pin_memory()
+    Sd, Cd, gSd, gCd = (torch.empty_like(x, device="cuda") for x in (S, C, S, C))
+    nlld = torch.empty(B, dtype=torch.float64, device="cuda")
+    view = obs.view()
+    for _ in range(2):
+        _lib.check(_lib.lib.qmc_nll_fwd_bwd_gather_host(
+            Sh.data_ptr(), Ch.data_ptr(), Sd.data_ptr(), Cd.data_ptr(), C_.byref(view), C_.byref(lik), B, IJ, K, R,
+            _lib.QMC_ALGO_AUTO, obs.tile_warps, nlld.data_ptr(), gSd.data_ptr(), gCd.data_ptr(), nllh.data_ptr(),
+            gSh.data_ptr(), gCh.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    np.testing.assert_allclose(nllh.numpy(), want[0].cpu().numpy(), rtol=1e-6)   # a chunk may pick another kernel than the whole batch
+    assert rel_err(gSh.numpy(), want[1].cpu().numpy()) < 1e-5
+    assert rel_err(gCh.numpy(), want[2].cpu().numpy()) < 1e-5
+
+
 def test_errors_are_loud(q):
     from quantized_spectrum_cartography_b200 import _lib
     S, C, Y, Wx, bb, sigma, off = _random_instance(1, 5, 5, 4, 2, 0.5, 4, seed=1)
