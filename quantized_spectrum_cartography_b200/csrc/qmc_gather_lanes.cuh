@@ -96,8 +96,10 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ bool lw_valid(uint32_t w) { return w < 0xFF000000u; }
 __device__ __forceinline__ int lw_level(uint32_t w) { return (int)(((w >> 23) & 0xFEu) | (w >> 31)); }
 
-template <int RP, int EPI, bool LOGD, bool GRAD>
+// GMODE: 0 = NLL only, 1 = both gradients, 2 = gC only (QMC_SKIP_GS), 3 = gS only (QMC_SKIP_GC)
+template <int RP, int EPI, bool LOGD, int GMODE>
 __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams prm) {
+  constexpr bool GRAD = GMODE != 0;
   extern __shared__ __align__(16) float smem[];
   const int W = prm.tile_warps, K = prm.K;
   const int TP = prm.sub_pixels * W;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   const int nthr = blockDim.x;
   const float* __restrict__ Sb = prm.S + b * prm.sB;
   const float* __restrict__ Cb = prm.C + (int64_t)b * prm.R * K;
-  const bool do_gs = GRAD && prm.want_gs, do_gc = GRAD && prm.want_gc;  // uniform over the grid
+  constexpr bool do_gs = GMODE == 1 || GMODE == 3, do_gc = GMODE == 1 || GMODE == 2;
   float* gSb = do_gs ? prm.gS + b * prm.sB : nullptr;
   const bool bulk = (prm.sR == 1 && prm.sP == RP && prm.R == RP && (RP % 4) == 0 &&
                      ((reinterpret_cast<uintptr_t>(Sb) | (do_gs ? reinterpret_cast<uintptr_t>(gSb) : 0)) & 15) == 0);
@@ -358,21 +360,22 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
         g[j] = ok[j] ? ev.gx * dxdt : 0.0f;
       }
     }
-    if (GRAD) {
+    auto gc_step = [&](int j) {  // gC: registers only
+      if (RP % 2 == 0) {
+        const f2 g2 = bc2(g[j]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {  // gC: registers only
-        if (RP % 2 == 0) {
-          const f2 g2 = bc2(g[j]);
-#pragma unroll
-          for (int r = 0; r < RP; r += 2) {
-            const f2 a = fma2(g2, mk2(sv[j][r], sv[j][r + 1]), mk2(acc[r], acc[r + 1]));
-            un2(a, acc[r], acc[r + 1]);
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < RP; ++r) acc[r] = fmaf(g[j], sv[j][r], acc[r]);
+        for (int r = 0; r < RP; r += 2) {
+          const f2 a = fma2(g2, mk2(sv[j][r], sv[j][r + 1]), mk2(acc[r], acc[r + 1]));
+          un2(a, acc[r], acc[r + 1]);
         }
+      } else {
+#pragma unroll
+        for (int r = 0; r < RP; ++r) acc[r] = fmaf(g[j], sv[j][r], acc[r]);
       }
+    };
+    if (GRAD && !do_gs) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gc_step(j);
     }
     if (do_gs) {
 #pragma unroll
@@ -393,6 +396,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
 #pragma unroll
           for (int r = 0; r < RP; ++r) sts32_if(rs + r * 4, fmaf(g[j], c[r], lds32(rs + r * 4)), ok[j]);
         }
+        if (do_gc) gc_step(j);
       }
       __syncwarp();  // steps are applied in program order by the converged warp: a later step may touch the same pixel from another lane
     }
@@ -466,7 +470,12 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
 template <int RP, int EPI, bool LOGD, bool GRAD>
 static int launch_lanes_one(const GatherParams& prm, cudaStream_t st) {
   const size_t smem = lanes_smem_bytes(prm.K, RP, prm.sub_pixels, prm.tile_warps, GRAD);
-  auto kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD>;
+  auto kern = gather_lanes_kernel<RP, EPI, LOGD, 0>;
+  if (GRAD) {
+    if (prm.want_gs && prm.want_gc) kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 1 : 0>;
+    else if (prm.want_gc) kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 2 : 0>;
+    else kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 3 : 0>;
+  }
   QMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ctas = (int64_t)prm.B * prm.tiles_per_map;
   QMC_REQUIRE(ctas <= 0x7fffffff, "too many CTAs (%lld)", (long long)ctas);
