@@ -193,11 +193,18 @@ __global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict_
                                  int sub_pixels, int tile_warps, const int64_t* __restrict__ stream_off,
                                  uint32_t* __restrict__ words, int32_t* __restrict__ nrows,
                                  int32_t* __restrict__ overflow) {
-  extern __shared__ int16_t band_of_rank_all[];
+  extern __shared__ __align__(16) unsigned char lanes_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (s >= n_streams) return;
-  int16_t* band_of_rank = band_of_rank_all + wib * K;
+  // per warp: hist[32][G] u64 | band_of_rank[K16] i16 | lane_bands[32][G] i16 | assign[32] i16
+  const int K16 = (K + 15) & ~15;
+  const size_t per_warp = (size_t)32 * G * 8 + (size_t)K16 * 2 + (size_t)32 * G * 2 + 64;
+  unsigned char* wbase = lanes_smem + wib * per_warp;
+  unsigned long long* sh_hist = reinterpret_cast<unsigned long long*>(wbase);
+  int16_t* band_of_rank = reinterpret_cast<int16_t*>(wbase + (size_t)32 * G * 8);
+  int16_t* sh_bands = band_of_rank + K16;
+  int16_t* sh_assign = sh_bands + 32 * G;
   const int64_t row0 = s * K;
   const int64_t beg = row_off[row0];
   const int st = (int)(s % n_sub);
@@ -215,11 +222,74 @@ __global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict_
   }
   __syncwarp();
   int bands[G];
-  int left = 0;  // entries this lane still has to emit
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const int r = (g & 1) ? 32 * g + 31 - lane : 32 * g + lane;
     bands[g] = r < K ? band_of_rank[r] : -1;
+  }
+  // Regroup the 32 band sets into the four quarter-warps so that, phase by phase (g-th band of every
+  // lane), each quarter's supply of pixels per shared-memory bank group is as even as possible: a
+  // quarter-warp can avoid bank conflicts only while all eight groups are still in stock.
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    unsigned long long h = 0;
+    if (bands[g] >= 0) {
+      const int c0 = (int)(row_off[row0 + bands[g]] - beg), e0 = (int)(row_off[row0 + bands[g] + 1] - beg);
+      for (int qq = c0; qq < e0; ++qq) {
+        const int r = (idx[beg + qq] - bands[g] * IJ - p0) & 7;
+        if (((h >> (8 * r)) & 0xFFull) < 255) h += 1ull << (8 * r);
+      }
+    }
+    sh_hist[lane * G + g] = h;
+  }
+  __syncwarp();
+  {
+    const int myq = lane >> 3, myr = lane & 7;  // this lane keeps the running supply of (quarter, bank group)
+    int supply[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) supply[g] = 0;
+    int fill = 0;  // lanes already placed in this lane's quarter
+    for (int i = 0; i < 32; ++i) {
+      int add[G];
+      int cost = 0;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        add[g] = (int)((sh_hist[i * G + g] >> (8 * myr)) & 0xFFull);
+        int mx = supply[g] + add[g], mn = mx;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        cost += mx - mn;
+      }
+      if (fill >= 8) cost = 0x3fffffff;
+      int best = 0, bc = 0x7fffffff;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ck = __shfl_sync(0xffffffffu, cost, 8 * k);
+        if (ck < bc) { bc = ck; best = k; }
+      }
+      const int slot = __shfl_sync(0xffffffffu, fill, 8 * best);
+      if (myq == best) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) supply[g] += add[g];
+        ++fill;
+      }
+      if (lane == 0) sh_assign[i] = (int16_t)(8 * best + slot);
+    }
+  }
+  __syncwarp();
+  {
+    const int dst = sh_assign[lane];
+#pragma unroll
+    for (int g = 0; g < G; ++g) sh_bands[dst * G + g] = (int16_t)bands[g];
+  }
+  __syncwarp();
+  int left = 0;  // entries this lane still has to emit
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    bands[g] = sh_bands[lane * G + g];
     if (bands[g] >= 0) left += (int)(row_off[row0 + bands[g] + 1] - row_off[row0 + bands[g]]);
   }
   int g = -1, band = K, cur = 0, end = 0;  // band K: the dummy band of a lane that owns nothing
@@ -461,8 +531,9 @@ extern "C" int qmc_obs_build_lanes(int32_t* idx_rows_dev, uint8_t* lvl_rows_dev,
   const int64_t blocks = (n_streams + warps - 1) / warps;
   QMC_REQUIRE(blocks <= 0x7fffffff, "too many streams");
   QMC_CUDA_CHECK(cudaMemsetAsync(overflow_dev, 0, sizeof(int32_t), st));
-  const size_t smem = (size_t)warps * K * sizeof(int16_t);
   const int G = (K + 31) / 32;
+  const int Gt = G > 8 ? 8 : G;
+  const size_t smem = (size_t)warps * ((size_t)32 * Gt * 8 + (size_t)((K + 15) & ~15) * 2 + (size_t)32 * Gt * 2 + 64);
 #define QMC_LANES_GO(GG)                                                                                       \
   obs_lanes_kernel<GG><<<(unsigned)blocks, warps * 32, smem, st>>>(idx_rows_dev, lvl_rows_dev, row_off_dev,     \
                                                                    n_streams, K, IJ, n_sub, sub_pixels, tile_warps, \
