@@ -97,6 +97,11 @@ __device__ __forceinline__ bool lw_valid(uint32_t w) { return w < 0xFF000000u; }
 __device__ __forceinline__ int lw_level(uint32_t w) { return (int)(((w >> 23) & 0xFEu) | (w >> 31)); }
 
 // GMODE: 0 = NLL only, 1 = both gradients, 2 = gC only (QMC_SKIP_GS), 3 = gS only (QMC_SKIP_GC)
+// 64 KB of zeros in global memory (L2-resident in practice): source of the bulk copy that clears a warp's gS
+// slice, so the clearing costs neither issue slots nor shared-memory-pipe wavefronts
+constexpr uint32_t LANES_ZERO_BYTES = 64 * 1024;
+__device__ __align__(128) unsigned char g_lanes_zero[LANES_ZERO_BYTES];
+
 template <int RP, int EPI, bool LOGD, int GMODE>
 __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams prm) {
   constexpr bool GRAD = GMODE != 0;
@@ -131,11 +136,13 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   float* gSw = gSsm + (size_t)sl0 * RP;
 
   // ---- prologue: every warp stages its own slice; one CTA barrier for C -------------------------
+  const uint32_t slice_bytes = (uint32_t)sln * RP * sizeof(float);
+  const bool zero_by_copy = bulk && do_gs && slice_bytes <= LANES_ZERO_BYTES;
   if (bulk && sln > 0 && lane == 0) {
     mbar_init(&mbar[warp], 1);
-    const uint32_t bytes = (uint32_t)sln * RP * sizeof(float);
-    mbar_expect_tx(&mbar[warp], bytes);
-    bulk_g2s(Sw, Sb + (int64_t)(p0 + sl0) * RP, bytes, &mbar[warp]);
+    mbar_expect_tx(&mbar[warp], zero_by_copy ? 2 * slice_bytes : slice_bytes);
+    bulk_g2s(Sw, Sb + (int64_t)(p0 + sl0) * RP, slice_bytes, &mbar[warp]);
+    if (zero_by_copy) bulk_g2s(gSw, g_lanes_zero, slice_bytes, &mbar[warp]);
   }
   if (threadIdx.x == 0) done = 0;
   // every global load of the prologue is issued before anything waits on one of them (the warp issues in
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   if (GRAD) {
     if (RP % 4 == 0) {
       float4* z = reinterpret_cast<float4*>(gSw);
-      for (int i = lane; i < (do_gs ? sln * (RP / 4) : 0); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = lane; i < ((do_gs && !zero_by_copy) ? sln * (RP / 4) : 0); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       float4* zc = reinterpret_cast<float4*>(gCw + (size_t)warp * (K + 1) * RP);
       for (int i = lane; i < (K + 1) * (RP / 4); i += 32) zc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
