@@ -89,6 +89,16 @@ def main():
             out["tiled_entries_per_s"] = obs_t.nobs / (t * 1e-3)
             out["tiled_hbm_frac"] = obs_t.algorithmic_bytes(R) / (t * 1e-3) / 1e9 / peak
             out["tiled_geometry"] = {"tiles": n_sub // tw, "tile_warps": tw, "sub_pixels": sub}
+        if n_sub // tw >= 16 and 32 <= K <= 256:
+            n_sub_l, sub_l, tw_l = q.plan_tiles(IJ, K, R, lanes=True)
+            obs_l = q.build_obs(Y[0], Wx[0], K, IJ, 1, n_sub=n_sub_l, sub_pixels=sub_l, tile_warps=tw_l, lanes=True)
+            S_pm = S.transpose(1, 2).contiguous().transpose(1, 2)
+            t = timeit(lambda: q.nll_fwd_bwd(S_pm, C, obs_l, lik), flush=flush)
+            out["lanes_ms"] = t
+            out["lanes_entries_per_s"] = obs_l.nobs / (t * 1e-3)
+            out["lanes_hbm_frac"] = obs_f.algorithmic_bytes(R) / (t * 1e-3) / 1e9 / peak
+            out["lanes_geometry"] = {"tiles": n_sub_l // tw_l, "tile_warps": tw_l, "sub_pixels": sub_l,
+                                     "padding": round(obs_l.padding_fraction(), 4)}
         if dense.dense_supported(K, R):
             dobs = dense.pack_dense(Y[0], Wx[0], K)
             t = timeit(lambda: dense.nll_fwd_bwd_dense(S[0], C[0], dobs, lik), flush=flush)
@@ -102,6 +112,21 @@ def main():
             out["dense_vs_flat_gS_rel"] = float((b[1] - a[1][0]).norm() / a[1][0].norm())
             out["dense_vs_flat_gC_rel"] = float((b[2] - a[2][0]).norm() / a[2][0].norm())
         print(json.dumps(out))
+    if "cfg2" in args.cases.split(","):
+        # batched multi-bit maps: 256 x cfg2 through the lane-stream kernel (general epilogue, log domain)
+        from quantized_spectrum_cartography_b200 import qmc
+        B = 256
+        pb = qmc.synth_problem("cfg2", B, dev, seed=0)
+        obs, lik = pb["obs"], pb["lik"]
+        S = (0.8 * pb["maps"].S_true).transpose(1, 2).contiguous().transpose(1, 2)
+        C = pb["maps"].C_true.contiguous()
+        t = timeit(lambda: q.nll_fwd_bwd(S, C, obs, lik))
+        R = C.shape[1]
+        alg = obs.nobs * 5 + B * (2 * 4 * R * (S.shape[2] + C.shape[2]) + 4)
+        print(json.dumps({"case": "cfg2 x 256 batched", "layout": "lanes" if obs.lanes else "rows", "nobs": obs.nobs, "ms": t,
+                          "entries_per_s": obs.nobs / (t * 1e-3), "hbm_frac": alg / (t * 1e-3) / 1e9 / peak,
+                          "tile_warps": obs.tile_warps, "tiles_per_map": obs.n_sub // max(obs.tile_warps, 1),
+                          "padding": round(obs.padding_fraction(), 4)}))
 
 
 if __name__ == "__main__":
