@@ -201,14 +201,15 @@ def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: Solve
         check(lib.qmc_counter_add(ctr_ptr, 1, stream()))
         ss.copy_(ss_next)
 
-    def iteration():
+    def iteration(want_cost: bool = True):
         for j in range(cfg.c_inner):
             nll_fwd_bwd(S, Cf, obs, lik, out=(nll, gS, gC), skip_gs=True)
             update(Cf, gC, mC, vC, nC, ssC, ssC_next, cfg.lr_c, cfg.lam_c, cfg.project_c and j == cfg.c_inner - 1, ctr_c)
         cost = None
         for j in range(cfg.s_inner):
             nll_fwd_bwd(S, Cf, obs, lik, out=(nll, gS, gC), skip_gc=True)
-            cost = nll.to(torch.float32) + cfg.lam_s * ssS.sqrt().to(torch.float32)
+            if want_cost and j == cfg.s_inner - 1:   # the tracked quantity of the notebook (c1:209,214)
+                cost = nll.to(torch.float32) + cfg.lam_s * ssS.sqrt().to(torch.float32)
             update(S, gS, mS, vS, nS, ssS, ssS_next, cfg.lr_s, cfg.lam_s, cfg.project_s and j == cfg.s_inner - 1, ctr_s)
         return cost
 
@@ -224,15 +225,16 @@ def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: Solve
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_cost = iteration()
+                static_cost = iteration(bool(cfg.track_every))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for it in range(cfg.iters):
+            tracked = bool(cfg.track_every) and (it % cfg.track_every == 0 or it == cfg.iters - 1)
             if graph is not None:
                 graph.replay()
                 cost = static_cost
             else:
-                cost = iteration()
+                cost = iteration(tracked)
             if cfg.track_every and (it % cfg.track_every == 0 or it == cfg.iters - 1):
                 res.cost.append(cost.detach().clone())
                 if nmse_fn is not None:
