@@ -160,21 +160,26 @@ def lane_streams(obs: ObsSet) -> ObsSet:
     n_streams = obs.B * obs.n_sub
     per_stream = obs.row_off[:: obs.K][1:] - obs.row_off[:: obs.K][:-1]
     G = (obs.K + 31) // 32
-    rows_cap = (13 * per_stream * G) // (10 * obs.K) + 4 * G + 8
-    rows_cap = torch.clamp(((rows_cap + 3) // 4) * 4, min=16)     # the kernel loads the first four groups blindly
-    # one capacity for all streams (the largest): a stream's address then needs no table look-up, and a
-    # CTA can prefetch the data of the CTA that will follow it on its SM
-    stride = int(rows_cap.max().item()) * 32 if n_streams else 128
-    stream_off = torch.arange(n_streams + 1, dtype=torch.int64, device=dev) * stride
-    total = n_streams * stride
     with torch.cuda.device(dev):
-        words = torch.empty(total, dtype=torch.int32, device=dev)
         nrows = torch.empty(n_streams, dtype=torch.int32, device=dev)
         overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        check(lib.qmc_obs_build_lanes(obs.idx.data_ptr(), obs.lvl.data_ptr(), obs.row_off.data_ptr(), obs.B, obs.K,
-                                      obs.IJ, obs.n_sub, obs.sub_pixels, obs.tile_warps, stream_off.data_ptr(),
-                                      words.data_ptr(), nrows.data_ptr(), overflow.data_ptr(), _stream()))
-        if int(overflow.item()):
-            raise RuntimeError("lane-stream layout: a stream exceeded its capacity (pathological band/pixel structure)")
+        # capacity: 1.3x the even share of the busiest lane; dense sampling of small sub-tiles (every band
+        # wants the same few pixels in the same step) can need more -> retry with twice the room
+        for attempt in range(4):
+            slack = 13 << attempt
+            rows_cap = (slack * per_stream * G) // (10 * obs.K) + 4 * G + 8
+            rows_cap = torch.clamp(((rows_cap + 3) // 4) * 4, min=16)     # the kernel loads the first four groups blindly
+            # one capacity for all streams (the largest): a stream's address then needs no table look-up, and
+            # a CTA can prefetch the data of the CTA that will follow it on its SM
+            stride = int(rows_cap.max().item()) * 32 if n_streams else 512
+            stream_off = torch.arange(n_streams + 1, dtype=torch.int64, device=dev) * stride
+            words = torch.empty(max(n_streams * stride, 1), dtype=torch.int32, device=dev)
+            check(lib.qmc_obs_build_lanes(obs.idx.data_ptr(), obs.lvl.data_ptr(), obs.row_off.data_ptr(), obs.B, obs.K,
+                                          obs.IJ, obs.n_sub, obs.sub_pixels, obs.tile_warps, stream_off.data_ptr(),
+                                          words.data_ptr(), nrows.data_ptr(), overflow.data_ptr(), _stream()))
+            if not int(overflow.item()):
+                break
+        else:
+            raise RuntimeError("lane-stream layout: a stream exceeded 8x its expected length (pathological band/pixel structure)")
     return ObsSet(obs.idx, obs.lvl, obs.row_off, obs.B, obs.K, obs.IJ, obs.n_sub, obs.sub_pixels, obs.tile_warps,
                   obs.nobs, obs.max_level, words, stream_off, nrows, stride)

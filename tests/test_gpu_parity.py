@@ -348,6 +348,45 @@ def test_host_buffer_entry_point(q):
     assert rel_err(gCh.numpy(), want[2].cpu().numpy()) < 1e-5
 
 
+def test_lane_stream_edge_cases(q):
+    """Lane-stream layout at its edges: a map with no observation at all, a fully observed map, a band
+    that is never observed, the top level 254 in use, and an empty batch member at either end."""
+    from quantized_spectrum_cartography_b200 import _lib
+    B, I, J, K, R = 5, 13, 11, 32, 4
+    IJ = I * J
+    g = torch.Generator().manual_seed(5)
+    S = torch.rand(B, R, IJ, generator=g) * 0.1 + 0.01
+    C = torch.rand(B, R, K, generator=g) * 0.2 + 0.02
+    T = torch.einsum("brp,brk->bkp", S, C)
+    bb = torch.linspace(float(T.min()) * 0.5, float(T.max()) * 1.5, 256)       # 255 levels: 0..254
+    sigma = float(bb[1] - bb[0]) * 3
+    Y = oc.assign_levels(T + sigma * torch.randn(T.shape, generator=g), bb)
+    Y[1, 3, :7] = 254                                                            # the top level
+    Wx = torch.bernoulli(torch.full(T.shape, 0.3), generator=g)
+    Wx[0] = 0                                                                    # nothing observed
+    Wx[2] = 1                                                                    # everything observed
+    Wx[3, 5] = 0                                                                 # a band never observed
+    Wx[4] = 0
+    lik = q.make_likelihood(bb, sigma, log_domain=False, sentinels=False)
+    obs = q.make_obs(Y.cuda(), Wx.cuda(), K, "cuda", B=B, R=R, tiled=True, tile_warps=4, lanes=True)
+    assert obs.lanes and obs.max_level == 254 and obs.nobs == int(Wx.sum().item())
+    nll, gS, gC = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik)
+    assert nll[0].item() == 0.0 and nll[4].item() == 0.0
+    assert not gS[0].any() and not gC[0].any() and not gS[4].any() and not gC[4].any()
+    assert not gC[3, :, 5].any()
+    for b in (1, 2, 3):
+        want = oc.nll_and_grads_fp64(S[b].reshape(R, 1, I, J), C[b], Y[b].reshape(K, 1, I, J), Wx[b].reshape(K, 1, I, J),
+                                     bb, sigma, sentinels=False)
+        assert nll[b].item() == pytest.approx(want[0], rel=NLL_RTOL)
+        assert rel_err(gS[b].cpu().numpy(), want[1].reshape(R, -1)) < GRAD_RTOL
+        assert rel_err(gC[b].cpu().numpy(), want[2]) < GRAD_RTOL
+    # level 255 cannot be represented (it marks padding): loud, not silent
+    Y2 = Y.clone()
+    Y2[1, 0, 0] = 255
+    with pytest.raises(ValueError, match="254"):
+        q.make_obs(Y2.cuda(), torch.ones_like(Wx).cuda(), K, "cuda", B=B, R=R, tiled=True, tile_warps=4, lanes=True)
+
+
 @pytest.mark.parametrize("layout", ["flat", "tiled", "lanes"])
 def test_host_buffer_entry_point_pipelines_chunks(q, layout):
     """B >= 64: the host entry cuts the batch into chunks on three streams; every observation layout must
