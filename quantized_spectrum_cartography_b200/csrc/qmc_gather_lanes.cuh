@@ -267,12 +267,12 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     if (RP % 4 == 0) {
 #pragma unroll
       for (int r = 0; r < RP; r += 4) {
-        const float4 c4 = lds128(crow + r * 4);
+        const float4 c4 = lds128_ro(crow + r * 4);  // read-only tile: free to move above the pending gS updates
         c[r] = c4.x; c[r + 1] = c4.y; c[r + 2] = c4.z; c[r + 3] = c4.w;
       }
     } else {
 #pragma unroll
-      for (int r = 0; r < RP; ++r) c[r] = lds32(crow + r * 4);
+      for (int r = 0; r < RP; ++r) c[r] = lds32_ro(crow + r * 4);
     }
 #pragma unroll
     for (int r = 0; r < RP; ++r) acc[r] = 0.0f;
@@ -285,14 +285,47 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   const f2 nthr2 = bc2(-prm.thr), inva2 = bc2(prm.inv_a * kS);
   const f2 kg2 = bc2(kInvSqrtPi * prm.inv_a);
 
+  // The gS updates of a group are applied one group late, in the same straight-line block as the next
+  // group's likelihood: the read-modify-write chain (LDS -> FFMA2 -> STS, four in a row, ordered) then
+  // overlaps the arithmetic instead of stalling the warp on the short scoreboard.
+  uint32_t pw[4];   // words of the pending group (0xFF000000 = padding, pixel 0: nothing to store)
+  float pg[4];      // their g = dNLL/dx
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { pw[j] = 0xFF000000u; pg[j] = 0.0f; }
+  auto apply_pending = [&](const float (&cp)[RP]) {  // cp: the C row of the pending group
+    if (!do_gs) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t rs = S_a + gS_delta + (pw[j] & LW_PIX_MASK) * ROWB;
+      const bool pok = lw_valid(pw[j]);
+      if (RP % 4 == 0) {
+        const f2 g2 = bc2(pg[j]);
+#pragma unroll
+        for (int r = 0; r < RP; r += 4) {
+          float4 v = lds128(rs + r * 4);  // padding lanes read a real lane's row; only the store is predicated
+          const f2 a = fma2(g2, mk2(cp[r], cp[r + 1]), mk2(v.x, v.y));
+          const f2 bq = fma2(g2, mk2(cp[r + 2], cp[r + 3]), mk2(v.z, v.w));
+          un2(a, v.x, v.y);
+          un2(bq, v.z, v.w);
+          sts128_if(rs + r * 4, v, pok);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < RP; ++r) sts32_if(rs + r * 4, fmaf(pg[j], cp[r], lds32(rs + r * 4)), pok);
+      }
+    }
+  };
+
   auto group = [&](const uint4 wv) {
     const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
-    const uint32_t key = w[0] & LW_BAND_MASK;
-    if (key != cur_key) switch_band(key);  // lanes change band only at group boundaries
+    __syncwarp();  // steps are applied in program order by the converged warp (a later step may touch the same pixel from another lane)
     float g[4], sv[4][RP];
     uint32_t srow[4];
     bool ok[4];
     float t[4];
+    // program order matters to ptxas (shared-memory loads are not moved above stores that may alias): this
+    // group's S rows and, on a band change, its C row are loaded first, then the pending gS updates are
+    // issued, and the arithmetic below fills their latency
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       ok[j] = lw_valid(w[j]);
@@ -307,6 +340,15 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
 #pragma unroll
         for (int r = 0; r < RP; ++r) sv[j][r] = lds32_ro(srow[j] + r * 4);
       }
+    }
+    float cp[RP];
+#pragma unroll
+    for (int r = 0; r < RP; ++r) cp[r] = c[r];
+    const uint32_t key = w[0] & LW_BAND_MASK;
+    if (key != cur_key) switch_band(key);  // lanes change band only at group boundaries
+    apply_pending(cp);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
       if (RP % 2 == 0) {
         f2 d = mul2(mk2(sv[j][0], sv[j][1]), mk2(c[0], c[1]));
 #pragma unroll
@@ -380,33 +422,12 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
         for (int r = 0; r < RP; ++r) acc[r] = fmaf(g[j], sv[j][r], acc[r]);
       }
     };
-    if (GRAD && !do_gs) {
+    if (do_gc) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) gc_step(j);
     }
-    if (do_gs) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t rs = srow[j] + gS_delta;
-        if (RP % 4 == 0) {
-          const f2 g2 = bc2(g[j]);
-#pragma unroll
-          for (int r = 0; r < RP; r += 4) {
-            float4 v = lds128(rs + r * 4);  // padding lanes read a real lane's row; only the store is predicated
-            const f2 a = fma2(g2, mk2(c[r], c[r + 1]), mk2(v.x, v.y));
-            const f2 bq = fma2(g2, mk2(c[r + 2], c[r + 3]), mk2(v.z, v.w));
-            un2(a, v.x, v.y);
-            un2(bq, v.z, v.w);
-            sts128_if(rs + r * 4, v, ok[j]);
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < RP; ++r) sts32_if(rs + r * 4, fmaf(g[j], c[r], lds32(rs + r * 4)), ok[j]);
-        }
-        if (do_gc) gc_step(j);
-      }
-      __syncwarp();  // steps are applied in program order by the converged warp: a later step may touch the same pixel from another lane
-    }
+    for (int j = 0; j < 4; ++j) { pw[j] = w[j]; pg[j] = g[j]; }
   };
 
   int slot = 0;
@@ -421,6 +442,9 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     group(wv);
   }
   cp_async_wait<0>();
+  __syncwarp();
+  apply_pending(c);
+  __syncwarp();
   switch_band((uint32_t)K << LW_BAND_SHIFT);  // flush the last band
 
   // ---- epilogue: own gS slice out, then the last warp folds gC and the NLL -----------------------
