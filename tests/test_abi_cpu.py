@@ -20,7 +20,8 @@ def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for must in ("qmc_quantize_levels", "qmc_obs_count_scan", "qmc_obs_fill", "qmc_nll_fwd_bwd_gather",
                  "qmc_nll_fwd_bwd_gather_host", "qmc_nll_fwd_bwd_dense", "qmc_dense_pack", "qmc_abi_version",
-                 "qmc_last_error"):
+                 "qmc_last_error", "qmc_obs_build_lanes", "qmc_lanes_smem_bytes", "qmc_adam_frob_project",
+                 "qmc_sumsq_per_map", "qmc_counter_add"):
         assert must in syms, must
 
 
@@ -67,3 +68,14 @@ def test_plan_tiles_covers_the_map():
         assert n_sub % tw == 0 and n_sub * sub >= IJ
         assert (n_sub - tw) * sub < IJ or n_sub == tw      # no entirely empty trailing tile
     assert plan_tiles(2601, 64, 4) == (8, 326, 8)          # cfg1/cfg3: one CTA per map
+    assert plan_tiles(2601, 64, 4, lanes=True) == (8, 326, 8)
+
+
+def test_lanes_tile_of_cfg3_leaves_room_for_two_ctas_per_sm():
+    """Lane-stream kernel at cfg1/cfg3: stream ring + S and gS tiles + C + 8 private gC copies; two CTAs
+    (plus 1 KB reserved each) must fit the 228 KB of an SM."""
+    from quantized_spectrum_cartography_b200 import _lib
+    b = _lib.lib.qmc_lanes_smem_bytes(64, 4, 326, 8)
+    assert b == (8 * 4 * 32 * 4 + 2 * 326 * 8 * 4 + 65 * 4 + 8 * 65 * 4) * 4 + 16
+    assert 2 * (b + 1024 + 512) <= 228 * 1024
+    assert _lib.lib.qmc_lanes_smem_bytes(64, 4, 100000, 8) == 0

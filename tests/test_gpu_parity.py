@@ -348,6 +348,44 @@ def test_host_buffer_entry_point(q):
     assert rel_err(gCh.numpy(), want[2].cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("n,lam,project", [(1028, 0.0, False), (1028, 2.5, True), (1031, 2.5, True), (3, 1.0, False)])
+def test_fused_update_matches_torch_adam(q, n, lam, project):
+    """qmc_adam_frob_project against torch.optim.Adam + autograd of lam*||p||_F + clamp_, five steps on the
+    same gradients (vector path n % 4 == 0, scalar path otherwise, a map shorter than a vector)."""
+    from quantized_spectrum_cartography_b200._lib import check, lib
+    B = 3
+    g0 = torch.Generator().manual_seed(n)
+    p0 = (torch.rand(B, n, generator=g0) - 0.3).cuda()
+    grads = [(torch.randn(B, n, generator=g0) * 0.1).cuda() for _ in range(5)]
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=3e-3)
+    for gk in grads:
+        opt.zero_grad()
+        loss = (ref * gk).sum() + lam * torch.linalg.vector_norm(ref, dim=1).sum()
+        loss.backward()
+        opt.step()
+        if project:
+            with torch.no_grad():
+                ref.clamp_(min=0)
+    p = p0.clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    ss, ss2 = torch.empty(B, dtype=torch.float64, device="cuda"), torch.empty(B, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.qmc_sumsq_per_map(p.data_ptr(), B, n, ss.data_ptr(), st))
+    np.testing.assert_allclose(ss.cpu().numpy(), (p0.double() ** 2).sum(1).cpu().numpy(), rtol=1e-12)
+    ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for k, gk in enumerate(grads):
+        # odd steps take the step number from the host, even steps from the device counter
+        host_step, dev = (k + 1, None) if k % 2 else (1, ctr.data_ptr())
+        check(lib.qmc_adam_frob_project(p.data_ptr(), gk.data_ptr(), m.data_ptr(), v.data_ptr(), B, n, ss.data_ptr(),
+                                        ss2.data_ptr(), 3e-3, 0.9, 0.999, 1e-8, lam, int(project), host_step, dev, st))
+        check(lib.qmc_counter_add(ctr.data_ptr(), 1, st))
+        ss.copy_(ss2)
+    assert int(ctr.item()) == 5
+    assert rel_err(p.cpu().numpy(), ref.detach().cpu().numpy()) < 2e-6
+    np.testing.assert_allclose(ss.cpu().numpy(), (p.double() ** 2).sum(1).cpu().numpy(), rtol=1e-9)
+
+
 def test_lane_stream_edge_cases(q):
     """Lane-stream layout at its edges: a map with no observation at all, a fully observed map, a band
     that is never observed, the top level 254 in use, and an empty batch member at either end."""
