@@ -251,6 +251,20 @@ QMC_API int qmc_adam_frob_project(float* p_dev, const float* g_dev, float* m_dev
                           float beta1, float beta2, float eps, float lam, int project, int step,
                           const int32_t* step_dev, void* stream);
 
+/* The S-step of the alternating solver in ONE launch (lane-stream observation set, S stored pixel-major,
+ * R a multiple of 4, one tile per map): evaluates the likelihood at (S, C), keeps the gS tile in shared
+ * memory and applies qmc_adam_frob_project's update to S, m, v in place from there -- gS never goes to
+ * HBM.  nll_out_dev: NLL at the S the call was entered with.  sumsq_in/out as in qmc_adam_frob_project
+ * (sumsq_out must not alias sumsq_in).  Returns QMC_ERR_UNSUPPORTED for any other layout: run
+ * qmc_nll_fwd_bwd_gather + qmc_adam_frob_project instead.  qmc/qmc.ipynb c1:199-212 with S in place of
+ * generator(Z). */
+QMC_API int qmc_solver_s_step_fused(float* S_dev, int64_t s_stride_b, int64_t s_stride_r, int64_t s_stride_p,
+                            const float* C_dev, const qmc_obs_view_t* obs, const qmc_likelihood_t* lik,
+                            int B, int IJ, int K, int R, int tile_warps, double* nll_out_dev, float* m_dev,
+                            float* v_dev, const double* sumsq_in_dev, double* sumsq_out_dev, float lr,
+                            float beta1, float beta2, float eps, float lam, int project, int step,
+                            const int32_t* step_dev, void* stream);
+
 /* *counter_dev += add on the stream (the step counter of a CUDA-graph-captured solver iteration). */
 QMC_API int qmc_counter_add(int32_t* counter_dev, int add, void* stream);
 

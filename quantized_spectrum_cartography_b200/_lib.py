@@ -52,6 +52,8 @@ SIGNATURES = {
     "qmc_sumsq_per_map": (_I, [_P, _I, _L, _P, _P]),
     "qmc_adam_frob_project": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _F, _F, _F, _F, _F, _I, _I, _P, _P]),
     "qmc_counter_add": (_I, [_P, _I, _P]),
+    "qmc_solver_s_step_fused": (_I, [_P, _L, _L, _L, _P, C.POINTER(ObsView), C.POINTER(Likelihood), _I, _I, _I, _I, _I,
+                                     _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I, _I, _P, _P]),
     "qmc_nll_fwd_bwd_gather": (_I, [_P, _L, _L, _L, _P, C.POINTER(ObsView), C.POINTER(Likelihood),
                                     _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "qmc_tiled_smem_bytes": (_L, [_I, _I, _I, _I]),

@@ -32,11 +32,23 @@ extern "C" int64_t qmc_tiled_smem_bytes(int K, int R, int sub_pixels, int tile_w
   return b <= 227 * 1024 ? (int64_t)b : 0;
 }
 
-extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, int64_t s_stride_r,
-                                      int64_t s_stride_p, const float* C_dev, const qmc_obs_view_t* obs,
-                                      const qmc_likelihood_t* lik, int B, int IJ, int K, int R, int algo,
-                                      int tile_warps, double* nll_out_dev, float* gS_out_dev,
-                                      float* gC_out_dev, void* stream) {
+namespace {
+struct FusedUpdate {  // qmc_solver_s_step_fused
+  float* S_rw;
+  float* m;
+  float* v;
+  const double* ss_in;
+  double* ss_out;
+  float lr, beta1, beta2, eps, lam;
+  int project, step;
+  const int32_t* step_dev;
+};
+}  // namespace
+
+static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_r, int64_t s_stride_p,
+                       const float* C_dev, const qmc_obs_view_t* obs, const qmc_likelihood_t* lik, int B, int IJ,
+                       int K, int R, int algo, int tile_warps, double* nll_out_dev, float* gS_out_dev,
+                       float* gC_out_dev, void* stream, const FusedUpdate* fu) {
   QMC_REQUIRE(S_dev && C_dev && obs && lik && nll_out_dev, "null argument");
   const bool lanes = obs->words_dev != nullptr;
   QMC_REQUIRE(lanes ? ((obs->stream_off_dev || obs->stream_stride > 0) && obs->nrows_dev)
@@ -53,7 +65,7 @@ extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, in
   const bool lanes_set = obs->words_dev != nullptr;
   const bool want_gs = grad && !(lanes_set && (lik->flags & QMC_SKIP_GS));
   const bool want_gc = grad && !(lanes_set && (lik->flags & QMC_SKIP_GC));
-  QMC_REQUIRE((!want_gs || gS_out_dev) && (!want_gc || gC_out_dev), "a requested gradient output is NULL");
+  QMC_REQUIRE(fu || ((!want_gs || gS_out_dev) && (!want_gc || gC_out_dev)), "a requested gradient output is NULL");
   cudaStream_t st = (cudaStream_t)stream;
 
   GatherParams prm;
@@ -63,6 +75,16 @@ extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, in
   prm.stream_stride = lanes ? obs->stream_stride : 0;
   prm.lookahead = 0;
   prm.want_gs = want_gs; prm.want_gc = want_gc;
+  prm.fuse_update = fu != nullptr;
+  prm.S_rw = nullptr; prm.adam_m = nullptr; prm.adam_v = nullptr; prm.ss_in = nullptr; prm.ss_out = nullptr;
+  prm.lr = prm.beta1 = prm.beta2 = prm.eps = prm.lam = 0.0f;
+  prm.project = prm.step = 0; prm.step_dev = nullptr;
+  if (fu) {
+    prm.S_rw = fu->S_rw; prm.adam_m = fu->m; prm.adam_v = fu->v; prm.ss_in = fu->ss_in; prm.ss_out = fu->ss_out;
+    prm.lr = fu->lr; prm.beta1 = fu->beta1; prm.beta2 = fu->beta2; prm.eps = fu->eps; prm.lam = fu->lam;
+    prm.project = fu->project; prm.step = fu->step; prm.step_dev = fu->step_dev;
+    prm.want_gs = 1; prm.want_gc = 0;
+  }
   prm.nll = nll_out_dev; prm.gS = gS_out_dev; prm.gC = gC_out_dev;
   prm.n_sub = obs->n_sub; prm.sub_pixels = obs->sub_pixels;
   prm.B = B; prm.IJ = IJ; prm.K = K; prm.R = R;
@@ -168,4 +190,37 @@ extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, in
   }
 #undef QMC_RP_CASE
   return set_error(QMC_ERR_UNSUPPORTED, "rank %d", R);
+}
+
+extern "C" int qmc_nll_fwd_bwd_gather(const float* S_dev, int64_t s_stride_b, int64_t s_stride_r,
+                                      int64_t s_stride_p, const float* C_dev, const qmc_obs_view_t* obs,
+                                      const qmc_likelihood_t* lik, int B, int IJ, int K, int R, int algo,
+                                      int tile_warps, double* nll_out_dev, float* gS_out_dev,
+                                      float* gC_out_dev, void* stream) {
+  return gather_impl(S_dev, s_stride_b, s_stride_r, s_stride_p, C_dev, obs, lik, B, IJ, K, R, algo, tile_warps,
+                     nll_out_dev, gS_out_dev, gC_out_dev, stream, nullptr);
+}
+
+extern "C" int qmc_solver_s_step_fused(float* S_dev, int64_t s_stride_b, int64_t s_stride_r, int64_t s_stride_p,
+                                       const float* C_dev, const qmc_obs_view_t* obs, const qmc_likelihood_t* lik,
+                                       int B, int IJ, int K, int R, int tile_warps, double* nll_out_dev,
+                                       float* m_dev, float* v_dev, const double* sumsq_in_dev,
+                                       double* sumsq_out_dev, float lr, float beta1, float beta2, float eps,
+                                       float lam, int project, int step, const int32_t* step_dev, void* stream) {
+  QMC_REQUIRE(S_dev && C_dev && obs && lik && nll_out_dev && m_dev && v_dev, "null argument");
+  QMC_REQUIRE(lam == 0.0f || sumsq_in_dev, "the Frobenius regulariser needs the squared norms of S");
+  QMC_REQUIRE(step >= 0 && (step > 0 || step_dev), "Adam steps count from 1");
+  QMC_REQUIRE(!sumsq_out_dev || sumsq_out_dev != sumsq_in_dev, "sumsq_out must not alias sumsq_in");
+  const bool layout_ok = obs->words_dev && R % 4 == 0 && R <= QMC_MAX_RANK && s_stride_r == 1 && s_stride_p == R &&
+                         s_stride_b == (int64_t)R * IJ && tile_warps > 0 && obs->n_sub == tile_warps &&
+                         !(lik->flags & QMC_FORWARD_ONLY) &&
+                         ((reinterpret_cast<uintptr_t>(S_dev) | reinterpret_cast<uintptr_t>(m_dev) |
+                           reinterpret_cast<uintptr_t>(v_dev)) & 15) == 0;
+  if (!layout_ok)
+    return set_error(QMC_ERR_UNSUPPORTED, "fused S-step needs a lane-stream observation set with one tile per map, "
+                                          "pixel-major S/m/v (16-byte aligned) and a rank that is a multiple of 4");
+  if (sumsq_out_dev) QMC_CUDA_CHECK(cudaMemsetAsync(sumsq_out_dev, 0, sizeof(double) * B, (cudaStream_t)stream));
+  FusedUpdate fu{S_dev, m_dev, v_dev, sumsq_in_dev, sumsq_out_dev, lr, beta1, beta2, eps, lam, project, step, step_dev};
+  return gather_impl(S_dev, s_stride_b, s_stride_r, s_stride_p, C_dev, obs, lik, B, IJ, K, R, QMC_ALGO_LANES, tile_warps,
+                     nll_out_dev, nullptr, nullptr, stream, &fu);
 }

@@ -21,6 +21,16 @@ struct GatherParams {
   int64_t stream_stride;      // lane-stream layout: > 0 = uniform stream capacity in words (no table look-up)
   int lookahead;              // lanes kernel: CTAs resident on the device (prefetch distance in CTAs)
   int want_gs, want_gc;       // lanes kernel: which gradients the caller needs (QMC_SKIP_GS / QMC_SKIP_GC)
+  // fused S-step (qmc_solver_s_step_fused): S is updated in place from the gS tile in shared memory
+  int fuse_update;
+  float* S_rw;                // = S
+  float* adam_m;
+  float* adam_v;
+  const double* ss_in;
+  double* ss_out;
+  float lr, beta1, beta2, eps, lam;
+  int project, step;
+  const int32_t* step_dev;
   double* nll;
   float* gS;
   float* gC;

@@ -96,7 +96,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ bool lw_valid(uint32_t w) { return w < 0xFF000000u; }
 __device__ __forceinline__ int lw_level(uint32_t w) { return (int)(((w >> 23) & 0xFEu) | (w >> 31)); }
 
-// GMODE: 0 = NLL only, 1 = both gradients, 2 = gC only (QMC_SKIP_GS), 3 = gS only (QMC_SKIP_GC)
+// GMODE: 0 = NLL only, 1 = both gradients, 2 = gC only (QMC_SKIP_GS), 3 = gS only (QMC_SKIP_GC),
+//        4 = gS only, consumed in place by the fused Adam update of S (qmc_solver_s_step_fused)
 // 64 KB of zeros in global memory (L2-resident in practice): source of the bulk copy that clears a warp's gS
 // slice, so the clearing costs neither issue slots nor shared-memory-pipe wavefronts
 constexpr uint32_t LANES_ZERO_BYTES = 64 * 1024;
@@ -125,10 +126,11 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   const int nthr = blockDim.x;
   const float* __restrict__ Sb = prm.S + b * prm.sB;
   const float* __restrict__ Cb = prm.C + (int64_t)b * prm.R * K;
-  constexpr bool do_gs = GMODE == 1 || GMODE == 3, do_gc = GMODE == 1 || GMODE == 2;
-  float* gSb = do_gs ? prm.gS + b * prm.sB : nullptr;
+  constexpr bool do_gs = GMODE == 1 || GMODE == 3 || GMODE == 4, do_gc = GMODE == 1 || GMODE == 2;
+  constexpr bool FUSE = GMODE == 4;  // bulk layout guaranteed by the host
+  float* gSb = (do_gs && !FUSE) ? prm.gS + b * prm.sB : nullptr;
   const bool bulk = (prm.sR == 1 && prm.sP == RP && prm.R == RP && (RP % 4) == 0 &&
-                     ((reinterpret_cast<uintptr_t>(Sb) | (do_gs ? reinterpret_cast<uintptr_t>(gSb) : 0)) & 15) == 0);
+                     ((reinterpret_cast<uintptr_t>(Sb) | ((do_gs && !FUSE) ? reinterpret_cast<uintptr_t>(gSb) : 0)) & 15) == 0);
   // this warp's pixel slice of the tile
   const int sl0 = min(warp * prm.sub_pixels, np);
   const int sln = min((warp + 1) * prm.sub_pixels, np) - sl0;
@@ -186,6 +188,14 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       const int s20 = min(warp * prm.sub_pixels, np2), s2n = min((warp + 1) * prm.sub_pixels, np2) - s20;
       const char* s2 = reinterpret_cast<const char*>(prm.S + b2 * prm.sB + (int64_t)(tile2 * TP + s20) * RP);
       for (int o = lane * 128; o < s2n * RP * 4; o += 32 * 128) prefetch_l2(s2 + o);
+    }
+  }
+  if (FUSE && sln > 0) {  // the Adam moments of this warp's slice are needed at the very end: pull them into L2 now
+    const char* m2 = reinterpret_cast<const char*>(prm.adam_m + b * prm.sB + (int64_t)(p0 + sl0) * RP);
+    const char* v2 = reinterpret_cast<const char*>(prm.adam_v + b * prm.sB + (int64_t)(p0 + sl0) * RP);
+    for (int o = lane * 128; o < (int)slice_bytes; o += 32 * 128) {
+      prefetch_l2(m2 + o);
+      prefetch_l2(v2 + o);
     }
   }
   if (!bulk) {
@@ -455,7 +465,52 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   }
   const double wsumv = warp_sum((double)nll_part);
   if (lane == 0) wsum[warp] = wsumv;
-  if (do_gs && sln > 0) {
+  if (FUSE && sln > 0) {
+    // Adam + regulariser + projection on this warp's slice, straight from the S and gS tiles in shared
+    // memory: p, m, v are contiguous in the pixel-major storage
+    __syncwarp();
+    const int tstep = prm.step + (prm.step_dev ? *prm.step_dev : 0);
+    const float bc1 = 1.0f - powf(prm.beta1, (float)tstep), bc2 = 1.0f - powf(prm.beta2, (float)tstep);
+    const float step_size = prm.lr / bc1, bc2_sqrt = sqrtf(bc2);
+    const float nrm = (float)sqrt(prm.ss_in ? prm.ss_in[b] : 0.0);
+    const float coef = (prm.lam != 0.0f && nrm > 0.0f) ? prm.lam / nrm : 0.0f;
+    const float omb1 = 1.0f - prm.beta1, omb2 = 1.0f - prm.beta2;
+    const bool proj = prm.project != 0;
+    const int64_t goff = b * prm.sB + (int64_t)(p0 + sl0) * RP;
+    float4* __restrict__ pg4 = reinterpret_cast<float4*>(prm.S_rw + goff);
+    float4* __restrict__ mg4 = reinterpret_cast<float4*>(prm.adam_m + goff);
+    float4* __restrict__ vg4 = reinterpret_cast<float4*>(prm.adam_v + goff);
+    const float4* ps4 = reinterpret_cast<const float4*>(Sw);
+    const float4* gs4 = reinterpret_cast<const float4*>(gSw);
+    const int nvec = sln * (RP / 4);
+    double accsq = 0.0;
+    constexpr int FU = 4;  // vectors per lane in flight
+    for (int i0 = lane; i0 < nvec; i0 += 32 * FU) {
+      float4 mm[FU], vv[FU];
+#pragma unroll
+      for (int u = 0; u < FU; ++u) {
+        const int i = i0 + 32 * u;
+        if (i < nvec) { mm[u] = mg4[i]; vv[u] = vg4[i]; }
+      }
+#pragma unroll
+      for (int u = 0; u < FU; ++u) {
+        const int i = i0 + 32 * u;
+        if (i < nvec) {
+          float4 pp = ps4[i];
+          const float4 gg = gs4[i];
+          pp.x = adam_one(pp.x, gg.x, mm[u].x, vv[u].x, coef, omb1, prm.beta2, omb2, step_size, bc2_sqrt, prm.eps, proj);
+          pp.y = adam_one(pp.y, gg.y, mm[u].y, vv[u].y, coef, omb1, prm.beta2, omb2, step_size, bc2_sqrt, prm.eps, proj);
+          pp.z = adam_one(pp.z, gg.z, mm[u].z, vv[u].z, coef, omb1, prm.beta2, omb2, step_size, bc2_sqrt, prm.eps, proj);
+          pp.w = adam_one(pp.w, gg.w, mm[u].w, vv[u].w, coef, omb1, prm.beta2, omb2, step_size, bc2_sqrt, prm.eps, proj);
+          pg4[i] = pp; mg4[i] = mm[u]; vg4[i] = vv[u];
+          accsq += (double)pp.x * pp.x + (double)pp.y * pp.y + (double)pp.z * pp.z + (double)pp.w * pp.w;
+        }
+      }
+    }
+    accsq = warp_sum(accsq);
+    if (lane == 0 && prm.ss_out) atomicAdd(prm.ss_out + b, accsq);
+  }
+  if (do_gs && !FUSE && sln > 0) {
     if (bulk) {
       fence_async_smem();  // generic-proxy writes to the slice -> visible to the bulk-copy engine
       __syncwarp();
@@ -495,7 +550,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       }
     }
   }
-  if (do_gs && bulk && sln > 0 && lane == 0) bulk_wait_all();  // the slice must stay alive until the engine has read it
+  if (do_gs && !FUSE && bulk && sln > 0 && lane == 0) bulk_wait_all();  // the slice must stay alive until the engine has read it
 }
 
 template <int RP, int EPI, bool LOGD, bool GRAD>
@@ -503,7 +558,8 @@ static int launch_lanes_one(const GatherParams& prm, cudaStream_t st) {
   const size_t smem = lanes_smem_bytes(prm.K, RP, prm.sub_pixels, prm.tile_warps, GRAD);
   auto kern = gather_lanes_kernel<RP, EPI, LOGD, 0>;
   if (GRAD) {
-    if (prm.want_gs && prm.want_gc) kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 1 : 0>;
+    if (prm.fuse_update && RP % 4 == 0) kern = gather_lanes_kernel<RP, EPI, LOGD, (GRAD && RP % 4 == 0) ? 4 : 0>;
+    else if (prm.want_gs && prm.want_gc) kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 1 : 0>;
     else if (prm.want_gc) kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 2 : 0>;
     else kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 3 : 0>;
   }

@@ -30,17 +30,6 @@ struct AdamParams {
   int project;
 };
 
-__device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, float coef, float one_m_b1, float b2,
-                                          float one_m_b2, float step_size, float bc2_sqrt, float eps, bool project) {
-  const float gg = fmaf(coef, p, g);             // d/dp (nll + lam*||p||_F) = g + lam*p/||p||
-  m = fmaf(gg - m, one_m_b1, m);                 // exp_avg.lerp_(grad, 1 - beta1)
-  v = fmaf(one_m_b2 * gg, gg, v * b2);           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-  const float denom = sqrtf(v) / bc2_sqrt + eps; // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
-  float pn = p - step_size * (m / denom);        // param.addcdiv_(exp_avg, denom, value=-step_size)
-  if (project && pn < 0.0f) pn = 0.0f;           // X[X < 0] = 0
-  return pn;
-}
-
 template <bool VEC>
 __global__ void __launch_bounds__(UPD_THREADS) adam_frob_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                                 float* __restrict__ m, float* __restrict__ v, int64_t n,

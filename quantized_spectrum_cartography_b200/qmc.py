@@ -148,7 +148,8 @@ def solve_lowrank(S0: torch.Tensor, C0: torch.Tensor, nll_fn: Callable[[torch.Te
 
 
 def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: SolverConfig = SolverConfig(),
-                        nmse_fn: Optional[Callable] = None, betas=(0.9, 0.999), eps: float = 1e-8) -> SolverResult:
+                        nmse_fn: Optional[Callable] = None, betas=(0.9, 0.999), eps: float = 1e-8,
+                        fuse_s_step: bool = True) -> SolverResult:
     """The iteration of :func:`solve_lowrank` without autograd and without torch.optim: every step is
     one fused likelihood evaluation (``fused.nll_fwd_bwd``) followed by one fused update
     (``qmc_adam_frob_project``: regulariser gradient, Adam, projection, next squared norm) -- four
@@ -156,7 +157,10 @@ def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: Solve
     rounding (``tests/test_gpu_parity.py::test_fused_solver_matches_torch_solver``).
 
     ``S0`` may be emitter-major contiguous or pixel-major storage viewed as ``[B,R,IJ]``; the result
-    comes back in the same layout (internally S lives pixel-major when R is a multiple of 4).  ``cfg.cuda_graph`` captures one iteration (the Adam step number then lives on the device)."""
+    comes back in the same layout (internally S lives pixel-major when R is a multiple of 4).  With a
+    lane-stream observation set (one tile per map) the S-step is a single launch
+    (``qmc_solver_s_step_fused``: the update is applied from the gS tile in shared memory);
+    ``fuse_s_step=False`` keeps evaluation and update apart.  ``cfg.cuda_graph`` captures one iteration (the Adam step number then lives on the device)."""
     import ctypes as C
     from . import _lib
     from ._lib import check, lib
@@ -187,6 +191,9 @@ def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: Solve
     nll = torch.empty(B, dtype=torch.float64, device=dev)
     ssS, ssS_next = (torch.empty(B, dtype=torch.float64, device=dev) for _ in range(2))   # ||S_b||_F^2
     ssC, ssC_next = (torch.empty(B, dtype=torch.float64, device=dev) for _ in range(2))
+    view = obs.view()
+    fused_s = bool(fuse_s_step and obs.lanes and R % 4 == 0 and obs.n_sub == obs.tile_warps and not lik.flags & _lib.QMC_FORWARD_ONLY
+                   and S.stride(1) == 1 and S.stride(2) == R)
     ctr = torch.zeros(2, dtype=torch.int32, device=dev)          # Adam steps taken on C, on S
     ctr_c, ctr_s = ctr.data_ptr(), ctr.data_ptr() + 4
     res = SolverResult(S, Cf)
@@ -207,6 +214,18 @@ def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: Solve
             update(Cf, gC, mC, vC, nC, ssC, ssC_next, cfg.lr_c, cfg.lam_c, cfg.project_c and j == cfg.c_inner - 1, ctr_c)
         cost = None
         for j in range(cfg.s_inner):
+            project = cfg.project_s and j == cfg.s_inner - 1
+            if fused_s:
+                # evaluation + update of S in one launch: the gS tile never leaves shared memory
+                check(lib.qmc_solver_s_step_fused(
+                    S.data_ptr(), S.stride(0), S.stride(1), S.stride(2), Cf.data_ptr(), C.byref(view), C.byref(lik), B, IJ,
+                    K, R, obs.tile_warps, nll.data_ptr(), mS.data_ptr(), vS.data_ptr(), ssS.data_ptr(), ssS_next.data_ptr(),
+                    cfg.lr_s, betas[0], betas[1], eps, cfg.lam_s, int(project), 1, ctr_s, stream()))
+                if want_cost and j == cfg.s_inner - 1:
+                    cost = nll.to(torch.float32) + cfg.lam_s * ssS.sqrt().to(torch.float32)
+                check(lib.qmc_counter_add(ctr_s, 1, stream()))
+                ssS.copy_(ssS_next)
+                continue
             nll_fwd_bwd(S, Cf, obs, lik, out=(nll, gS, gC), skip_gc=True)
             if want_cost and j == cfg.s_inner - 1:   # the tracked quantity of the notebook (c1:209,214)
                 cost = nll.to(torch.float32) + cfg.lam_s * ssS.sqrt().to(torch.float32)

@@ -646,6 +646,11 @@ def test_fused_solver_matches_torch_solver(q, K, tiled, pixel_major, graph):
     for na, nb in zip(a.nmse, b.nmse):
         np.testing.assert_allclose(nb.cpu().numpy().reshape(-1), na.cpu().numpy().reshape(-1), rtol=1e-4)
     assert (b.S >= 0).all() and (b.C >= 0).all()
+    # S-step in one launch (update applied from the gS tile in shared memory) vs evaluation + update apart
+    if obs.lanes and obs.n_sub == obs.tile_warps:
+        c2 = qmc.solve_lowrank_fused(S0, 1.1 * C.cuda(), obs, lik, cfg_f, qmc.cuda_nmse_fn(T), fuse_s_step=False)
+        assert rel_err(c2.S.cpu().numpy(), b.S.cpu().numpy()) < 1e-6
+        assert rel_err(c2.C.cpu().numpy(), b.C.cpu().numpy()) < 1e-6
 
 
 @pytest.mark.parametrize("B,I,J,K,R,levels,log_domain,f,tw,n_tiles", [
