@@ -50,23 +50,10 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) {
 }
 __device__ __forceinline__ f2 bc2(float x) { return mk2(x, x); }
 
-// ---- predicated shared-memory accesses ------------------------------------------------------------
-// the load leaves its registers undefined when predicated off: only for values that are then stored
-// under the same predicate
-__device__ __forceinline__ float4 lds128_if(uint32_t a, bool p) {
-  float4 v;
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "r"((int)p) : "memory");
-  return v;
-}
+// ---- predicated shared-memory stores (padding lanes) ----------------------------------------------
 __device__ __forceinline__ void sts128_if(uint32_t a, float4 v, bool p) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
                ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)p) : "memory");
-}
-__device__ __forceinline__ float lds32_if(uint32_t a, bool p) {
-  float v;
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.f32 %0, [%1];\n\t}" : "=f"(v) : "r"(a), "r"((int)p) : "memory");
-  return v;
 }
 __device__ __forceinline__ void sts32_if(uint32_t a, float v, bool p) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" ::"r"(a), "f"(v), "r"((int)p) : "memory");
