@@ -378,7 +378,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
         v, nmaps, secs = cpu_reference_sample(wl["host_sample"], wl["I"], wl["J"], K, R, args.cpu_seconds)
         vf, nmaps_f, secs_f = cpu_reference_sample(wl["host_sample"], wl["I"], wl["J"], K, R,
                                                    min(4.0, args.cpu_seconds), vectorised=True)
