@@ -5,7 +5,8 @@
   masks separately and adding must equal evaluating their union;
 * batch consistency -- a map evaluated inside the 4096-map launch equals the same map evaluated alone
   with the other kernel, and permuting the maps permutes the outputs;
-* path agreement -- gather-flat, gather-tiled and dense-tcgen05 agree on the same instance;
+* path agreement -- gather-flat, gather-tiled, gather-lanes and dense-tcgen05 agree on the same instance;
+* reproducibility -- the lanes and tiled kernels use no atomics at one tile per map: bitwise equal reruns;
 * a sampled subset of maps against the float64 oracle.
 """
 import numpy as np
@@ -39,6 +40,61 @@ def _one_bit_problem(q, B, I, J, K, R, f, seed):
     Y = assign_levels(T + thr * torch.randn(T.shape, device=dev, generator=gen), bb).to(torch.uint8)
     Wx = torch.bernoulli(torch.full(T.shape, f, device=dev), generator=gen)
     return maps, Y, Wx, bb, thr
+
+
+def test_cfg3_full_batch_lanes_kernel(q):
+    """cfg3 through the headline path (lane-stream layout, gather_lanes_kernel, S pixel-major): agreement
+    with the tiled kernel on all 4096 maps, additivity over a mask split, map permutation, bitwise
+    reproducibility over repeated launches (no atomics: any shared-memory race would show up here), both S
+    storage orders, the single-gradient modes, and sampled maps against the float64 oracle."""
+    from quantized_spectrum_cartography_b200 import _lib
+    B, I, J, K, R = 4096, 51, 51, 64, 4
+    IJ = I * J
+    maps, Y, Wx, bb, sigma = _one_bit_problem(q, B, I, J, K, R, 0.10, seed=0)
+    lik = q.make_likelihood(bb, sigma)
+    S, C = (0.8 * maps.S_true).contiguous(), maps.C_true.contiguous()
+    S_pm = S.transpose(1, 2).contiguous().transpose(1, 2)
+    build = lambda y, w: q.make_obs(y, w, K, y.device, B=y.shape[0], R=R, tiled=True, lanes=True)
+    obs = build(Y, Wx)
+    assert obs.lanes and obs.n_sub == obs.tile_warps == 8 and obs.padding_fraction() < 0.12
+    nll, gS, gC = q.nll_fwd_bwd(S_pm, C, obs, lik)
+    assert torch.isfinite(nll).all() and torch.isfinite(gS).all() and torch.isfinite(gC).all()
+    # the previous headline kernel on the same batch
+    n_sub, sub, tw = q.plan_tiles(IJ, K, R)
+    obs_t = q.build_obs(Y, Wx, K, IJ, B, n_sub=n_sub, sub_pixels=sub, tile_warps=tw, bank_mod=q.bank_mod_for_rank(R))
+    t = q.nll_fwd_bwd(S, C, obs_t, lik, algo=_lib.QMC_ALGO_TILED)
+    assert torch.allclose(nll, t[0], rtol=1e-6)
+    assert rel(gS, t[1]) < 1e-5 and rel(gC, t[2]) < 1e-5
+    worst = ((gS - t[1]).flatten(1).norm(dim=1) / t[1].flatten(1).norm(dim=1)).max().item()
+    assert worst < 1e-4, worst                                   # every single map, not only the batch norm
+    # bitwise reproducible, launch after launch
+    for _ in range(5):
+        again = q.nll_fwd_bwd(S_pm, C, obs, lik)
+        assert torch.equal(again[0], nll) and torch.equal(again[1], gS) and torch.equal(again[2], gC)
+    # emitter-major S (the reference's layout) takes the transposing staging path: same arithmetic
+    e = q.nll_fwd_bwd(S, C, obs, lik)
+    assert torch.equal(e[0], nll) and torch.equal(e[1], gS.contiguous()) and torch.equal(e[2], gC)
+    # one gradient at a time (the solver's C-step and S-step)
+    c_only = q.nll_fwd_bwd(S_pm, C, obs, lik, skip_gs=True)
+    s_only = q.nll_fwd_bwd(S_pm, C, obs, lik, skip_gc=True)
+    assert torch.equal(c_only[2], gC) and torch.equal(s_only[1], gS) and torch.equal(c_only[0], nll) and torch.equal(s_only[0], nll)
+    # additivity over a split of the mask (different streams, different padding, same sums)
+    half = (torch.rand(Wx.shape, device=Wx.device, generator=torch.Generator(device=Wx.device).manual_seed(5)) < 0.5).float()
+    a = q.nll_fwd_bwd(S_pm, C, build(Y, Wx * half), lik)
+    b = q.nll_fwd_bwd(S_pm, C, build(Y, Wx * (1 - half)), lik)
+    assert torch.allclose(a[0] + b[0], nll, rtol=5e-7)
+    assert rel(a[1] + b[1], gS) < 1e-5 and rel(a[2] + b[2], gC) < 1e-5
+    # permuting the maps permutes the outputs, bitwise
+    perm = torch.randperm(B, device=S.device, generator=torch.Generator(device=S.device).manual_seed(6))
+    p = q.nll_fwd_bwd(S_pm[perm].transpose(1, 2).contiguous().transpose(1, 2), C[perm].contiguous(),
+                      build(Y[perm].contiguous(), Wx[perm].contiguous()), lik)
+    assert torch.equal(p[0], nll[perm]) and torch.equal(p[1], gS[perm]) and torch.equal(p[2], gC[perm])
+    for m in (0, 2048, B - 1):
+        want = oc.nll_and_grads_fp64(S[m].cpu().reshape(R, 1, I, J), C[m].cpu(), Y[m].cpu().long().reshape(K, 1, I, J),
+                                     Wx[m].cpu().reshape(K, 1, I, J), bb, sigma)
+        assert abs(nll[m].item() / want[0] - 1) < 1e-5
+        assert np.linalg.norm(gS[m].cpu().numpy() - want[1].reshape(R, -1)) / np.linalg.norm(want[1]) < 1e-4
+        assert np.linalg.norm(gC[m].cpu().numpy() - want[2]) / np.linalg.norm(want[2]) < 1e-4
 
 
 def test_cfg3_full_batch_properties(q):
