@@ -174,16 +174,23 @@ __device__ __forceinline__ BinEval probit_bin_reference(float lo, float hi, floa
 }
 
 // ---- one element of the fused factor update (qmc_solver.cu; also the tail of the fused S-step) ----------
-// torch.optim.Adam (no amsgrad, no weight decay) operation by operation in fp32, preceded by the gradient
-// of lam*||p||_F (coef = lam/||p||) and followed by the projection onto p >= 0.
+// torch.optim.Adam (no amsgrad, no weight decay) in fp32, preceded by the gradient of lam*||p||_F
+// (coef = lam/||p||) and followed by the projection onto p >= 0.  Same operations as torch; the square
+// root and the quotient use the SFU (sqrt.approx, rcp.approx: ~2^-22 relative) and the bias correction is
+// passed as its reciprocal, which keeps the update at a dozen instructions per element.
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, float coef, float one_m_b1, float b2,
-                                          float one_m_b2, float step_size, float bc2_sqrt, float eps, bool project) {
-  const float gg = fmaf(coef, p, g);             // d/dp (nll + lam*||p||_F) = g + lam*p/||p||
-  m = fmaf(gg - m, one_m_b1, m);                 // exp_avg.lerp_(grad, 1 - beta1)
-  v = fmaf(one_m_b2 * gg, gg, v * b2);           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-  const float denom = sqrtf(v) / bc2_sqrt + eps; // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
-  float pn = p - step_size * (m / denom);        // param.addcdiv_(exp_avg, denom, value=-step_size)
-  if (project && pn < 0.0f) pn = 0.0f;           // X[X < 0] = 0
+                                          float one_m_b2, float step_size, float inv_bc2_sqrt, float eps, bool project) {
+  const float gg = fmaf(coef, p, g);                         // d/dp (nll + lam*||p||_F) = g + lam*p/||p||
+  m = fmaf(gg - m, one_m_b1, m);                             // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(one_m_b2 * gg, gg, v * b2);                       // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  const float denom = fmaf(sqrt_approx(v), inv_bc2_sqrt, eps);  // exp_avg_sq.sqrt() / bias_correction2_sqrt + eps
+  float pn = fmaf(-step_size * m, rcp_approx(denom), p);     // param.addcdiv_(exp_avg, denom, value=-step_size)
+  if (project && pn < 0.0f) pn = 0.0f;                       // X[X < 0] = 0
   return pn;
 }
 

@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     __syncwarp();
     const int tstep = prm.step + (prm.step_dev ? *prm.step_dev : 0);
     const float bc1 = 1.0f - powf(prm.beta1, (float)tstep), bc2 = 1.0f - powf(prm.beta2, (float)tstep);
-    const float step_size = prm.lr / bc1, bc2_sqrt = sqrtf(bc2);
+    const float step_size = prm.lr / bc1, bc2_sqrt = 1.0f / sqrtf(bc2);  // reciprocal: see adam_one
     const float nrm = (float)sqrt(prm.ss_in ? prm.ss_in[b] : 0.0);
     const float coef = (prm.lam != 0.0f && nrm > 0.0f) ? prm.lam / nrm : 0.0f;
     const float omb1 = 1.0f - prm.beta1, omb2 = 1.0f - prm.beta2;

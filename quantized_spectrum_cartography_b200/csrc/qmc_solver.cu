@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(UPD_THREADS) adam_frob_kernel(float* __restric
   const int b = blockIdx.y;
   const int t = a.step + (a.step_dev ? *a.step_dev : 0);
   const float bc1 = 1.0f - powf(a.beta1, (float)t), bc2 = 1.0f - powf(a.beta2, (float)t);
-  const float step_size = a.lr / bc1, bc2_sqrt = sqrtf(bc2);
+  const float step_size = a.lr / bc1, bc2_sqrt = 1.0f / sqrtf(bc2);  // reciprocal: see adam_one
   const double ss = sumsq_in ? sumsq_in[b] : 0.0;
   const float nrm = (float)sqrt(ss);
   const float coef = (a.lam != 0.0f && nrm > 0.0f) ? a.lam / nrm : 0.0f;
