@@ -109,14 +109,17 @@ def nll_fwd_bwd(S3: torch.Tensor, C3: torch.Tensor, obs: ObsSet, lik: Likelihood
             if want_grad and (gS.stride() != S3.stride() or not gC.is_contiguous()):
                 raise ValueError("out buffers must have the strides of S3 (gS) and be contiguous (gC)")
         else:
+            # a gradient the lane-stream kernel is told to skip is neither computed nor allocated
+            need_gs = want_grad and not (skip_gs and obs.lanes)
+            need_gc = want_grad and not (skip_gc and obs.lanes)
             nll = torch.empty(B, dtype=torch.float64, device=S3.device)
-            gS = torch.empty_strided(S3.shape, S3.stride(), dtype=torch.float32, device=S3.device) if want_grad else None
-            gC = torch.empty_like(C3) if want_grad else None
+            gS = torch.empty_strided(S3.shape, S3.stride(), dtype=torch.float32, device=S3.device) if need_gs else None
+            gC = torch.empty_like(C3) if need_gc else None
         view = obs.view()
         check(lib.qmc_nll_fwd_bwd_gather(
             S3.data_ptr(), S3.stride(0), S3.stride(1), S3.stride(2), C3.data_ptr(), C.byref(view), C.byref(lik),
             B, IJ, K, R, algo, obs.tile_warps, nll.data_ptr(),
-            gS.data_ptr() if want_grad else None, gC.data_ptr() if want_grad else None, _stream()))
+            gS.data_ptr() if gS is not None else None, gC.data_ptr() if gC is not None else None, _stream()))
     return nll, gS, gC
 
 
@@ -124,10 +127,13 @@ class _QmcNll(torch.autograd.Function):
     @staticmethod
     def forward(ctx, S3, C3, obs, lik, algo):
         want = S3.requires_grad or C3.requires_grad
-        nll, gS, gC = nll_fwd_bwd(S3.detach(), C3.detach(), obs, lik, algo=algo, want_grad=want)
+        # the alternating solvers differentiate with respect to one factor at a time (qmc.ipynb c1:145,204:
+        # the other one is detached): the lane-stream kernel then skips the gradient nobody asked for
+        nll, gS, gC = nll_fwd_bwd(S3.detach(), C3.detach(), obs, lik, algo=algo, want_grad=want,
+                                  skip_gs=want and not S3.requires_grad, skip_gc=want and not C3.requires_grad)
         ctx.has_grad = want
         if want:
-            ctx.save_for_backward(gS, gC)
+            ctx.save_for_backward(*(x if x is not None else nll.new_empty(0) for x in (gS, gC)))
         return nll
 
     @staticmethod
