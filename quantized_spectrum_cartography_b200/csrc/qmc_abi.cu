@@ -135,13 +135,14 @@ extern "C" int qmc_nmse_terms(const float* S_dev, const float* C_dev, const floa
 // that the host->device copy of one chunk, the kernel of the previous one and the device->host copy of
 // the one before overlap (PCIe is full duplex; the kernel is a small fraction of either copy).
 namespace {
-struct HostPipe {
-  int dev = -1;
+struct HostPipe {  // per device: three copy/compute streams and the event that orders them after the caller's
+  std::mutex mu;   // calls on one device are serialised; different devices proceed independently
+  bool ready = false;
   cudaStream_t s[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t start = nullptr;
 };
-HostPipe g_pipe;
-std::mutex g_pipe_mu;
+constexpr int kMaxDevices = 64;
+HostPipe g_pipes[kMaxDevices];
 }  // namespace
 
 extern "C" int qmc_nll_fwd_bwd_gather_host(const float* S_host, const float* C_host, float* S_scratch_dev,
@@ -154,17 +155,15 @@ extern "C" int qmc_nll_fwd_bwd_gather_host(const float* S_host, const float* C_h
   const bool grad = !(lik->flags & QMC_FORWARD_ONLY);
   QMC_REQUIRE(!grad || (gS_host && gC_host && gS_scratch_dev && gC_scratch_dev), "null gradient buffers");
   cudaStream_t st = (cudaStream_t)stream;
-  std::lock_guard<std::mutex> lock(g_pipe_mu);
   int dev = 0;
   QMC_CUDA_CHECK(cudaGetDevice(&dev));
-  if (g_pipe.dev != dev) {
-    for (auto& x : g_pipe.s) {
-      if (x) cudaStreamDestroy(x);
-      QMC_CUDA_CHECK(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
-    }
-    if (g_pipe.start) cudaEventDestroy(g_pipe.start);
+  QMC_REQUIRE(dev >= 0 && dev < kMaxDevices, "device ordinal %d out of range", dev);
+  HostPipe& g_pipe = g_pipes[dev];
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  if (!g_pipe.ready) {
+    for (auto& x : g_pipe.s) QMC_CUDA_CHECK(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
     QMC_CUDA_CHECK(cudaEventCreateWithFlags(&g_pipe.start, cudaEventDisableTiming));
-    g_pipe.dev = dev;
+    g_pipe.ready = true;
   }
   QMC_CUDA_CHECK(cudaEventRecord(g_pipe.start, st));
   for (auto& x : g_pipe.s) QMC_CUDA_CHECK(cudaStreamWaitEvent(x, g_pipe.start, 0));
