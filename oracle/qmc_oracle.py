@@ -199,6 +199,53 @@ def nll_and_grads(S, C, Y, Wx, bin_boundaries, noise_std, offset=None, sentinels
     return nll.detach(), S.grad.detach(), C.grad.detach()
 
 
+
+# ----------------------------------------------------------------------------------------
+# SURVEY 8(f)(4)  masked least-squares baseline on the de-quantised mid-points
+# ----------------------------------------------------------------------------------------
+def masked_lsq(S, C, Y, Wx, bin_boundaries, offset=None, vectorised=False):
+    """The baseline cost of qmc_dowjons.ipynb c1:84,108-112 without the regularisers:
+
+        Obs   = get_quantized_obs_from_ordinal(Y, bb, std)          # bin mid-points
+        T_hat = get_tensor(S, C).unsqueeze(1); [T_hat = log(T_hat + offset)]
+        cost  = torch.norm(Wx * (T_hat - Obs)) ** 2
+
+    The boundary table is used as it is (quantization_model_log.py:44-46 leaves the sentinel
+    lines commented out)."""
+    Obs = get_quantized_obs_from_ordinal(Y, bin_boundaries)
+    T_hat = (get_tensor_vectorised if vectorised else get_tensor)(S, C).unsqueeze(1)
+    if offset is not None:
+        T_hat = torch.log(T_hat + offset)
+    return torch.norm(Wx * (T_hat - Obs)) ** 2
+
+
+def lsq_and_grads(S, C, Y, Wx, bin_boundaries, offset=None, vectorised=False):
+    """fp32 least-squares cost and its autograd gradients w.r.t. S and C (``cost.backward()`` of
+    qmc_dowjons.ipynb c1:114,132 without the regularisers)."""
+    S = S.detach().clone().requires_grad_(True)
+    C = C.detach().clone().requires_grad_(True)
+    cost = masked_lsq(S, C, Y, Wx, bin_boundaries, offset, vectorised)
+    cost.backward()
+    return cost.detach(), S.grad.detach(), C.grad.detach()
+
+
+def lsq_and_grads_fp64(S, C, Y, Wx, bin_boundaries, offset=None):
+    """float64 statement of the same cost with analytic gradients (observed entries selected, not
+    multiplied): d cost/d x = 2 (x - mid).  Returns (cost, gS [R,1,I,J], gC [R,K])."""
+    S64 = np.asarray(S.detach().cpu().numpy(), dtype=np.float64)
+    C64 = np.asarray(C.detach().cpu().numpy(), dtype=np.float64)
+    R, K = C64.shape
+    Smat = S64.reshape(R, -1)
+    Yk = np.asarray(Y.detach().cpu().numpy()).reshape(K, -1)
+    obs = np.asarray(Wx.detach().cpu().numpy()).reshape(K, -1) != 0
+    bb = np.asarray(bin_boundaries.detach().cpu().numpy(), dtype=np.float64)
+    T = C64.T @ Smat
+    X = np.log(T + float(offset)) if offset is not None else T
+    d = np.where(obs, X - 0.5 * (bb[Yk] + bb[Yk + 1]), 0.0)
+    gT = 2.0 * d / (T + float(offset)) if offset is not None else 2.0 * d
+    return float(np.sum(d * d)), (C64 @ gT).reshape(S64.shape), Smat @ gT.T
+
+
 def stable_logP_fp64(zl: np.ndarray, zu: np.ndarray):
     """float64 log P and (exp(-zu^2) - exp(-zl^2)) / P for P = 0.5*(erf(zu) - erf(zl)), zl < zu,
     evaluated without cancellation or underflow: both bounds in the right tail -> scaled

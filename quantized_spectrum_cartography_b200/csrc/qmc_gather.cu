@@ -58,7 +58,7 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
   QMC_REQUIRE(R <= QMC_MAX_RANK, "rank %d > %d", R, QMC_MAX_RANK);
   QMC_REQUIRE((int64_t)K * IJ < (1LL << 31), "K*IJ = %lld does not fit the int32 linear index", (long long)K * IJ);
   QMC_REQUIRE(lik->n_bounds >= 2 && lik->n_bounds <= QMC_MAX_BOUNDS, "n_bounds %d out of range", lik->n_bounds);
-  QMC_REQUIRE(lik->noise_std > 0.0f, "noise_std must be positive");
+  QMC_REQUIRE(lik->noise_std > 0.0f || (lik->flags & QMC_EPI_LSQ), "noise_std must be positive");
   QMC_REQUIRE(obs->n_sub > 0 && obs->sub_pixels > 0 && (int64_t)obs->n_sub * obs->sub_pixels >= IJ,
               "sub-tiles (%d x %d) do not cover IJ=%d", obs->n_sub, obs->sub_pixels, IJ);
   const bool grad = !(lik->flags & QMC_FORWARD_ONLY);
@@ -95,7 +95,7 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
   while ((1LL << l) < IJ) ++l;
   prm.div_magic = (uint32_t)(((1ULL << (31 + l)) / (uint64_t)IJ) + 1ULL);
   prm.div_shift = l - 1;
-  const float a = probit_scale(lik->noise_std);
+  const float a = (lik->flags & QMC_EPI_LSQ) ? 1.0f : probit_scale(lik->noise_std);  // least squares has no noise model
   prm.inv_a = 1.0f / a;
   prm.offset = lik->offset;
   for (int i = 0; i < lik->n_bounds; ++i) prm.bounds[i] = lik->bounds[i];
@@ -103,7 +103,8 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
 
   // epilogue: reference-literal, one-bit fast path (both outer bounds numerically infinite), or general
   int epi = EPI_STABLE;
-  if (lik->flags & QMC_EPI_REFERENCE) epi = EPI_REFERENCE;
+  if (lik->flags & QMC_EPI_LSQ) epi = EPI_LSQ;
+  else if (lik->flags & QMC_EPI_REFERENCE) epi = EPI_REFERENCE;
   else if (lik->n_bounds == 3) {
     // erfc(z) == 0 exactly (even in double) for z > 27; require the sentinel to sit that far out for
     // any |x| < half its magnitude

@@ -44,7 +44,7 @@ struct GatherParams {
   float bounds[QMC_MAX_BOUNDS];
 };
 
-enum : int { EPI_STABLE = 0, EPI_REFERENCE = 1, EPI_ONEBIT = 2 };
+enum : int { EPI_STABLE = 0, EPI_REFERENCE = 1, EPI_ONEBIT = 2, EPI_LSQ = 3 };
 
 __device__ __forceinline__ int fast_div(uint32_t n, uint32_t magic, int shift) {
   return (int)(__umulhi(n, magic) >> shift);
@@ -59,7 +59,15 @@ __device__ __forceinline__ BinEval eval_entry(const GatherParams& prm, float t, 
     x = logf(u);
     dxdt = 1.0f / u;
   }
-  if (EPI == EPI_ONEBIT) {
+  if (EPI == EPI_LSQ) {
+    // masked least squares on the bin mid-point (quantization_model_log.py:43-51, qmc_dowjons.ipynb c1:112):
+    // "logp" = -(x - mid)^2 so that the callers' nll -= logp accumulates the squared residual
+    const float d = x - 0.5f * (prm.bounds[lvl] + prm.bounds[lvl + 1]);
+    BinEval o;
+    o.logp = -d * d;
+    o.gx = 2.0f * d;
+    return o;
+  } else if (EPI == EPI_ONEBIT) {
     return probit_one_sided_fast(prm.thr, lvl ? -prm.inv_a : prm.inv_a, x);
   } else if (EPI == EPI_REFERENCE) {
     return probit_bin_reference(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
@@ -175,6 +183,10 @@ template <int RP> int launch_lanes_rp(const GatherParams& prm, int epi, bool log
       case EPI_REFERENCE:                                                            \
         if (logd) { if (grad) GO(EPI_REFERENCE, true, true); else GO(EPI_REFERENCE, true, false); }    \
         else { if (grad) GO(EPI_REFERENCE, false, true); else GO(EPI_REFERENCE, false, false); }       \
+        break;                                                                       \
+      case EPI_LSQ:                                                                  \
+        if (logd) { if (grad) GO(EPI_LSQ, true, true); else GO(EPI_LSQ, true, false); }                \
+        else { if (grad) GO(EPI_LSQ, false, true); else GO(EPI_LSQ, false, false); }                   \
         break;                                                                       \
       default:                                                                       \
         if (logd) { if (grad) GO(EPI_STABLE, true, true); else GO(EPI_STABLE, true, false); }          \

@@ -37,13 +37,18 @@ def _as_float(v) -> float:
 
 def make_likelihood(bin_boundaries, noise_std, *, offset=None, log_domain: Optional[bool] = None,
                     sentinels: Optional[bool] = None, reference_epilogue: bool = False,
-                    forward_only: bool = False) -> Likelihood:
+                    forward_only: bool = False, least_squares: bool = False) -> Likelihood:
     """Pack the model the way the reference's two files define it.
 
     ``offset is None`` -> linear-domain file: no log link, outer boundaries replaced by -/+1e5
     (quantization_model.py:31-33).  ``offset`` given -> log-domain file: x = log(t + offset),
     boundaries used as they are (quantization_model_log.py:32-34).  ``log_domain`` / ``sentinels``
-    override either default.  The caller's table is never modified (the reference clones it)."""
+    override either default.  The caller's table is never modified (the reference clones it).
+
+    ``least_squares=True`` selects the masked least-squares baseline on the bin mid-points instead of
+    the likelihood (qmc_dowjons.ipynb c1:112; quantization_model_log.py:43-51): ``noise_std`` is not
+    used and the table is taken as it is (the reference's mid-point function never substitutes
+    sentinels) unless ``sentinels=True`` is passed explicitly."""
     bb = torch.as_tensor(bin_boundaries, dtype=torch.float32).detach().cpu().reshape(-1).clone()
     n = bb.numel()
     if not 2 <= n <= _lib.QMC_MAX_BOUNDS:
@@ -51,14 +56,14 @@ def make_likelihood(bin_boundaries, noise_std, *, offset=None, log_domain: Optio
     if log_domain is None:
         log_domain = offset is not None
     if sentinels is None:
-        sentinels = not log_domain
+        sentinels = not log_domain and not least_squares
     if sentinels:
         bb[0], bb[-1] = -REF_SENTINEL, REF_SENTINEL
     lik = Likelihood()
     lik.n_bounds = n
     lik.flags = ((_lib.QMC_LOG_DOMAIN if log_domain else 0) | (_lib.QMC_EPI_REFERENCE if reference_epilogue else 0)
-                 | (_lib.QMC_FORWARD_ONLY if forward_only else 0))
-    lik.noise_std = _as_float(noise_std)
+                 | (_lib.QMC_FORWARD_ONLY if forward_only else 0) | (_lib.QMC_EPI_LSQ if least_squares else 0))
+    lik.noise_std = 1.0 if least_squares and noise_std is None else _as_float(noise_std)
     lik.offset = 0.0 if offset is None else _as_float(offset)
     for i, v in enumerate(bb.tolist()):
         lik.bounds[i] = v
@@ -194,6 +199,31 @@ def qmc_nll(S, C_, Y, Wx, bin_boundaries, noise_std, offset=None, log_domain=Non
     C3d = C_.reshape(1, R, K).to(device=dev, dtype=torch.float32)
     nll = _QmcNll.apply(S3d, C3d, obs, lik, _lib.QMC_ALGO_AUTO)
     return nll[0].to(dtype=torch.float32, device=S.device)
+
+
+def qmc_lsq(S, C_, Y, Wx, bin_boundaries, offset=None, log_domain=None, obs: Optional[ObsSet] = None,
+            device=None) -> torch.Tensor:
+    """The masked least-squares baseline as one fused call: drop-in for
+
+        Obs   = get_quantized_obs_from_ordinal(Y, bin_boundaries, std)
+        T_hat = get_tensor(S, C).unsqueeze(1); [T_hat = torch.log(T_hat + offset)]
+        cost  = torch.norm(Wx * (T_hat - Obs)) ** 2
+
+    (qmc_dowjons.ipynb c1:84,108-112).  Same shapes, dtypes, caching and autograd behaviour as
+    :func:`qmc_nll`; the observed-entry kernels run with the least-squares epilogue."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("qmc_lsq needs a CUDA device: this package has no CPU implementation")
+    dev = torch.device(device) if device is not None else (S.device if S.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+    R, K = C_.shape
+    S3 = S.reshape(1, R, -1)
+    IJ = S3.shape[2]
+    lik = make_likelihood(bin_boundaries, None, offset=offset, log_domain=log_domain, least_squares=True)
+    if obs is None:
+        obs = _cached_obs(Y, Wx, K, IJ, dev, R)
+    S3d = S3.to(device=dev, dtype=torch.float32)
+    C3d = C_.reshape(1, R, K).to(device=dev, dtype=torch.float32)
+    cost = _QmcNll.apply(S3d, C3d, obs, lik, _lib.QMC_ALGO_AUTO)
+    return cost[0].to(dtype=torch.float32, device=S.device)
 
 
 def make_obs(Y, Wx, K: Optional[int] = None, device=None, *, B: int = 1, R: Optional[int] = None,

@@ -72,3 +72,25 @@ def nll_case_inputs(nll_golden, fixture_instance, tag):
 def all_case_tags():
     g = load_golden("nll_cases.npz")
     return [str(t) for t in g["case_points"]]
+
+
+def lsq_case_names():
+    return [str(n) for n in load_golden("lsq_cases.npz")["names"]]
+
+
+def lsq_case_inputs(fixture_instance, name):
+    """One golden least-squares case (tests/golden/make_golden_lsq.py): inputs in the reference's
+    shapes plus the reference's own cost and gradients."""
+    g = load_golden("lsq_cases.npz")
+    K, I, J = 64, 51, 51
+    off = float(g[name + "_offset"])
+    Wx = torch.from_numpy(np.unpackbits(g[name + "_Wx"])[: K * I * J].astype(np.float32)).reshape(K, 1, I, J)
+    return {
+        "S": (float(g[name + "_scale"]) * fixture_instance["S_true"]).unsqueeze(1),
+        "C": fixture_instance["C_true"].clone(),
+        "Y": torch.from_numpy(g[name + "_Y"].astype(np.int64)),
+        "Wx": Wx,
+        "bb": torch.from_numpy(g[name + "_bb"]),
+        "offset": None if np.isnan(off) else off,
+        "obs_sub": g[name + "_obs_sub"], "cost": float(g[name + "_cost"]), "gS": g[name + "_gS"], "gC": g[name + "_gC"],
+    }

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import all_case_tags, load_golden, nll_case_inputs
+from conftest import all_case_tags, load_golden, lsq_case_inputs, lsq_case_names, nll_case_inputs
 from oracle import qmc_oracle as oc
 
 pytestmark = pytest.mark.gpu
@@ -739,3 +739,62 @@ def test_lane_stream_builder_and_kernel(q, B, I, J, K, R, levels, log_domain, f,
     nll_s, gS_s, gC_s = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik, out=(torch.empty_like(nll), gS.clone().zero_(), mark[1]), skip_gc=True)
     assert torch.equal(gC_s, torch.full_like(gC, 7.0)) and rel_err(gS_s.cpu().numpy(), gS.cpu().numpy()) < 1e-6
     np.testing.assert_allclose(nll_s.cpu().numpy(), nll.cpu().numpy(), rtol=1e-12)
+
+
+# ---- masked least-squares baseline on the de-quantised mid-points -----------------
+@pytest.mark.parametrize("name", lsq_case_names())
+def test_least_squares_baseline_vs_reference(name, q, fixture_instance):
+    """qmc_lsq (one fused launch, autograd) against the reference's own run of the dowjons cost
+    (qmc_dowjons.ipynb c1:84,108-114): cost within 1e-5 relative, gradients within 1e-4."""
+    c = lsq_case_inputs(fixture_instance, name)
+    S = c["S"].cuda().requires_grad_(True)
+    C = c["C"].cuda().requires_grad_(True)
+    before = q._lib.launch_count()
+    cost = q.qmc_lsq(S, C, c["Y"], c["Wx"], c["bb"], offset=c["offset"])
+    cost.backward()
+    assert q._lib.launch_count() > before
+    assert cost.item() == pytest.approx(c["cost"], rel=NLL_RTOL)
+    assert rel_err(S.grad.cpu().numpy(), c["gS"]) < GRAD_RTOL
+    assert rel_err(C.grad.cpu().numpy(), c["gC"]) < GRAD_RTOL
+    # and against the float64 statement
+    want = oc.lsq_and_grads_fp64(c["S"], c["C"], c["Y"], c["Wx"], c["bb"], c["offset"])
+    assert cost.item() == pytest.approx(want[0], rel=NLL_RTOL)
+    assert rel_err(S.grad.cpu().numpy(), want[1]) < GRAD_RTOL
+    assert rel_err(C.grad.cpu().numpy(), want[2]) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("R,levels,log_domain", [(4, 2, False), (8, 8, True), (3, 5, True), (16, 16, False)])
+@pytest.mark.parametrize("algo", ["flat", "tiled", "lanes"])
+def test_least_squares_batched_all_kernels(q, R, levels, log_domain, algo):
+    """The least-squares epilogue in every observed-entry kernel: per-map cost and gradients equal the
+    float64 oracle's (ragged and empty maps included); the dense path refuses the flag."""
+    from quantized_spectrum_cartography_b200 import _lib, dense
+    B, I, J, K = 4, 17, 13, 32
+    S, C, Y, Wx, bb, sigma, off = _random_instance(B, I, J, K, R, 0.3, levels, seed=7 * R + levels, log_domain=log_domain)
+    Wx[1] = 0
+    Wx[2, :, : (I * J) // 2] = 0
+    lik = q.make_likelihood(bb, None, offset=off, least_squares=True)
+    IJ = I * J
+    if algo == "flat":
+        obs, a = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, B), _lib.QMC_ALGO_FLAT
+    elif algo == "tiled":
+        obs = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, B, n_sub=4, sub_pixels=-(-IJ // 4), tile_warps=2, bank_mod=q.bank_mod_for_rank(R))
+        a = _lib.QMC_ALGO_TILED
+    else:
+        obs = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, B, n_sub=4, sub_pixels=-(-IJ // 4), tile_warps=4, lanes=True)
+        a = _lib.QMC_ALGO_LANES
+    cost, gS, gC = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik, algo=a)
+    for b in range(B):
+        want = oc.lsq_and_grads_fp64(S[b].reshape(R, 1, I, J), C[b], Y[b].reshape(K, 1, I, J), Wx[b].reshape(K, 1, I, J), bb, off)
+        assert cost[b].item() == pytest.approx(want[0], rel=NLL_RTOL, abs=1e-12)
+        if Wx[b].sum() == 0:
+            assert gS[b].abs().max() == 0 and gC[b].abs().max() == 0
+            continue
+        assert rel_err(gS[b].cpu().numpy(), want[1].reshape(R, -1)) < GRAD_RTOL
+        assert rel_err(gC[b].cpu().numpy(), want[2]) < GRAD_RTOL
+    cost_f, _, _ = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik, algo=a, want_grad=False)
+    np.testing.assert_allclose(cost_f.cpu().numpy(), cost.cpu().numpy(), rtol=1e-12)
+    if algo == "flat" and R == 4:
+        dobs = dense.pack_dense(Y[0].cuda(), Wx[0].cuda(), K)
+        with pytest.raises(_lib.QmcError, match="least-squares"):
+            dense.nll_fwd_bwd_dense(S[0].cuda(), C[0].cuda(), dobs, lik)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import all_case_tags, load_golden, nll_case_inputs
+from conftest import all_case_tags, load_golden, lsq_case_inputs, lsq_case_names, nll_case_inputs
 from oracle import qmc_oracle as oc
 
 torch.set_num_threads(1)
@@ -115,3 +115,19 @@ def test_small_fry_matches_reference(fixture_instance):
     np.testing.assert_array_equal(oc.get_quantized_obs_from_ordinal(torch.arange(7), bb7).numpy(), m["midpoints"])
     assert oc.deterministic_cost(0.8 * S, C, 2 * target - 1, mean=5e-4).item() == pytest.approx(float(m["determ_cost"]), rel=1e-5)
     np.testing.assert_array_equal(oc.outer_band_loop(S[0, 0], C[0])[::8, ::5, ::5].numpy(), m["outer_sub"])
+
+
+@pytest.mark.parametrize("name", lsq_case_names())
+def test_least_squares_baseline_matches_reference(name, fixture_instance):
+    """oracle.masked_lsq against the reference's own run of qmc_dowjons.ipynb c1:84,108-114
+    (same fp32 op sequence -> the same numbers to rounding of the reduction order)."""
+    c = lsq_case_inputs(fixture_instance, name)
+    obs = oc.get_quantized_obs_from_ordinal(c["Y"], c["bb"])
+    np.testing.assert_array_equal(obs.numpy()[::8, :, ::5, ::5], c["obs_sub"])
+    cost, gS, gC = oc.lsq_and_grads(c["S"], c["C"], c["Y"], c["Wx"], c["bb"], c["offset"])
+    assert abs(cost.item() - c["cost"]) <= 1e-6 * abs(c["cost"])
+    np.testing.assert_allclose(gS.numpy(), c["gS"], rtol=1e-5, atol=1e-6 * np.abs(c["gS"]).max())
+    np.testing.assert_allclose(gC.numpy(), c["gC"], rtol=1e-5, atol=1e-6 * np.abs(c["gC"]).max())
+    # the vectorised statement gives the same cost
+    cost_v = oc.masked_lsq(c["S"], c["C"], c["Y"], c["Wx"], c["bb"], c["offset"], vectorised=True)
+    assert abs(cost_v.item() - c["cost"]) <= 1e-6 * abs(c["cost"])
