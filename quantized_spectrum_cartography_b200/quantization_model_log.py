@@ -8,13 +8,13 @@ from __future__ import annotations
 import torch
 
 from .constants import LOG_OFFSET_7_ADJUSTED as LOG_OFFSET
-from .fused import make_obs, qmc_nll as _qmc_nll
+from .fused import make_obs, qmc_lsq as _qmc_lsq, qmc_nll as _qmc_nll
 from .quantization_model import (DeterministicCost, F_probit, F_sigmoid, NMSE, NegLikelihood, _noisy, _prob_probit,  # noqa: F401
                                  _to_dev, assign_levels, dither_probit, dither_sigmoid, get_tensor, nmse_factors, outer)
 
 __all__ = ["quantize", "prob_probit", "get_quantized_obs_from_ordinal", "F_sigmoid", "dither_sigmoid", "F_probit",
            "dither_probit", "outer", "get_tensor", "NMSE", "NMSE_LOG", "NegLikelihood", "DeterministicCost",
-           "qmc_nll", "make_obs"]
+           "qmc_nll", "qmc_lsq", "make_obs"]
 
 
 def quantize(X, noise_std, bin_boundaries, offset=LOG_OFFSET):
@@ -45,3 +45,9 @@ def qmc_nll(S, C, Y, Wx, bin_boundaries, noise_std, offset=LOG_OFFSET, **kw):
     """Fused log-domain NLL: ``-sum(Wx*log(prob_probit(Y, log(get_tensor(S,C)+offset), bb, std)))``
     (qmc.ipynb c1:145-150) in one launch; see :func:`..fused.qmc_nll`."""
     return _qmc_nll(S, C, Y, Wx, bin_boundaries, noise_std, offset=offset, **kw)
+
+
+def qmc_lsq(S, C, Y, Wx, bin_boundaries, offset=LOG_OFFSET, **kw):
+    """Log-domain masked least squares on the bin mid-points: ``torch.norm(Wx*(log(get_tensor(S,C)+offset) -
+    get_quantized_obs_from_ordinal(Y, bb, std)))**2`` (qmc_dowjons.ipynb c1:84,108-112) in one launch."""
+    return _qmc_lsq(S, C, Y, Wx, bin_boundaries, offset=offset, **kw)

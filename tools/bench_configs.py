@@ -59,6 +59,7 @@ def problem(I, J, K, R, f, levels, log_domain, dev, seed=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="cfg1,cfg2,cfg4")
+    ap.add_argument("--lsq-maps", type=int, default=4096)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     peak = 6455.9
@@ -69,6 +70,8 @@ def main():
     shapes = {"cfg1": (51, 51, 64, 4, 0.10, 2, False), "cfg2": (101, 101, 128, 8, 0.20, 8, True),
               "cfg4": (512, 512, 256, 16, 0.50, 8, True)}
     for name in args.cases.split(","):
+        if name not in shapes:
+            continue
         I, J, K, R, f, levels, logd = shapes[name]
         IJ = I * J
         maps, Y, Wx, lik = problem(I, J, K, R, f, levels, logd, dev)
@@ -127,6 +130,23 @@ def main():
                           "entries_per_s": obs.nobs / (t * 1e-3), "hbm_frac": alg / (t * 1e-3) / 1e9 / peak,
                           "tile_warps": obs.tile_warps, "tiles_per_map": obs.n_sub // max(obs.tile_warps, 1),
                           "padding": round(obs.padding_fraction(), 4)}))
+    if "lsq" in args.cases.split(","):
+        # the masked least-squares baseline on the cfg3 batch (same observation set, same
+        # kernel, epilogue without the SFU chain) next to the likelihood on the same inputs
+        from quantized_spectrum_cartography_b200 import qmc
+        B = args.lsq_maps
+        pb = qmc.synth_problem("cfg1", B, dev, seed=0)          # cfg3 = B x cfg1
+        obs = pb["obs"]
+        S = (0.8 * pb["maps"].S_true).transpose(1, 2).contiguous().transpose(1, 2)
+        C = pb["maps"].C_true.contiguous()
+        R = C.shape[1]
+        alg = obs.nobs * 5 + B * (2 * 4 * R * (S.shape[2] + C.shape[2]) + 4)
+        lik_lsq = q.make_likelihood(pb["bb"], None, least_squares=True)
+        for name, lk in (("likelihood (one-bit probit)", pb["lik"]), ("least squares on bin mid-points", lik_lsq)):
+            t = timeit(lambda: q.nll_fwd_bwd(S, C, obs, lk))
+            print(json.dumps({"case": f"cfg3 x {B}", "epilogue": name, "layout": "lanes" if obs.lanes else "rows",
+                              "nobs": obs.nobs, "ms": t, "entries_per_s": obs.nobs / (t * 1e-3),
+                              "hbm_frac": alg / (t * 1e-3) / 1e9 / peak}))
 
 
 if __name__ == "__main__":
