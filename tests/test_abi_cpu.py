@@ -40,6 +40,32 @@ def test_python_binding_covers_every_declared_symbol():
     assert sorted(_lib.SIGNATURES) == declared_symbols()
 
 
+def test_python_flag_constants_mirror_the_header():
+    """Every flag of qmc_likelihood_t has the same value in _lib.py as in include/qmc_b200.h."""
+    from quantized_spectrum_cartography_b200 import _lib
+    text = open(HEADER).read()
+    flags = dict(re.findall(r"\b(QMC_(?:LOG_DOMAIN|EPI_\w+|FORWARD_ONLY|SKIP_\w+))\s*=\s*1u\s*<<\s*(\d+)", text))
+    assert {"QMC_LOG_DOMAIN", "QMC_EPI_REFERENCE", "QMC_FORWARD_ONLY", "QMC_SKIP_GS", "QMC_SKIP_GC", "QMC_EPI_LSQ"} <= set(flags)
+    for name, shift in flags.items():
+        assert getattr(_lib, name) == 1 << int(shift), name
+    assert len(set(flags.values())) == len(flags)
+
+
+def test_least_squares_likelihood_packing():
+    """make_likelihood(least_squares=True): flag set, table untouched (no sentinels: the reference's
+    mid-point function leaves them commented out, quantization_model_log.py:45-46), noise_std optional."""
+    import torch
+    from quantized_spectrum_cartography_b200 import _lib, make_likelihood
+    bb = torch.tensor([0.0, 0.25, 0.5, 1.0])
+    lik = make_likelihood(bb, None, least_squares=True)
+    assert lik.flags & _lib.QMC_EPI_LSQ and not lik.flags & _lib.QMC_LOG_DOMAIN
+    assert [lik.bounds[i] for i in range(4)] == [0.0, 0.25, 0.5, 1.0] and lik.noise_std > 0
+    lik = make_likelihood(bb, 0.1, offset=1e-3, least_squares=True)
+    assert lik.flags & _lib.QMC_EPI_LSQ and lik.flags & _lib.QMC_LOG_DOMAIN and lik.bounds[0] == 0.0
+    plain = make_likelihood(bb, 0.1)
+    assert not plain.flags & _lib.QMC_EPI_LSQ and plain.bounds[0] == -100000.0
+
+
 def test_argument_validation_needs_no_gpu():
     """Invalid arguments are rejected before any CUDA call, with a message."""
     from quantized_spectrum_cartography_b200 import _lib

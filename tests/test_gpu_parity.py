@@ -798,3 +798,34 @@ def test_least_squares_batched_all_kernels(q, R, levels, log_domain, algo):
         dobs = dense.pack_dense(Y[0].cuda(), Wx[0].cuda(), K)
         with pytest.raises(_lib.QmcError, match="least-squares"):
             dense.nll_fwd_bwd_dense(S[0].cuda(), C[0].cuda(), dobs, lik)
+
+
+def test_least_squares_solver_matches_torch_loop(q):
+    """The dowjons baseline loop (qmc_dowjons.ipynb c1:101-137 with S optimised directly): the fused solver
+    with the least-squares epilogue (fused S-step included) walks the trajectory of autograd on the oracle's
+    dense cost + torch.optim.Adam + clamp, map by map."""
+    from quantized_spectrum_cartography_b200 import qmc
+    B, I, J, K, R = 3, 20, 21, 64, 4
+    S, C, Y, Wx, bb, sigma, off = _random_instance(B, I, J, K, R, 0.3, 8, seed=91, log_domain=True)
+    lik = q.make_likelihood(bb, None, offset=off, least_squares=True)
+    obs = q.make_obs(Y.cuda(), Wx.cuda(), K, "cuda", B=B, R=R, tiled=True, tile_warps=4)
+    iters, lr_c, lr_s, lam = 8, 0.005, 0.001, 2.0
+    S0, C0 = 0.8 * S, 1.1 * C
+    cfg = qmc.SolverConfig(iters=iters, lr_c=lr_c, lr_s=lr_s, lam_c=lam, lam_s=lam, track_every=4)
+    got = qmc.solve_lowrank_fused(S0.cuda(), C0.cuda(), obs, lik, cfg)
+    for b in range(B):
+        Sb = S0[b].reshape(R, 1, I, J).clone().requires_grad_(True)
+        Cb = C0[b].clone().requires_grad_(True)
+        Yb, Wb = Y[b].reshape(K, 1, I, J), Wx[b].reshape(K, 1, I, J)
+        oC, oS = torch.optim.Adam([Cb], lr=lr_c), torch.optim.Adam([Sb], lr=lr_s)
+        for _ in range(iters):
+            for opt, par in ((oC, Cb), (oS, Sb)):
+                opt.zero_grad()
+                cost = (oc.masked_lsq(Sb, Cb, Yb, Wb, bb, off, vectorised=True)
+                        + lam * torch.norm(Cb, "fro") + lam * torch.norm(Sb, "fro"))
+                cost.backward()
+                opt.step()
+                with torch.no_grad():
+                    par.clamp_(min=0)
+        assert rel_err(got.S[b].cpu().numpy(), Sb.detach().reshape(R, -1).numpy()) < 1e-4
+        assert rel_err(got.C[b].cpu().numpy(), Cb.detach().numpy()) < 1e-4
