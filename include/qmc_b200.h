@@ -61,11 +61,15 @@ enum {
                                   updates and the write; other kernels ignore the flag.  gS_out may then be
                                   NULL for the lane-stream kernel only. */
   QMC_SKIP_GC = 1u << 4,       /* likewise for gC (the S-step, c1:199-212) */
-  QMC_EPI_LSQ = 1u << 5        /* masked least-squares baseline instead of the likelihood: every observed entry
+  QMC_EPI_LSQ = 1u << 5,       /* masked least-squares baseline instead of the likelihood: every observed entry
                                   contributes (x - (bounds[l] + bounds[l+1])/2)^2, the de-quantised mid-point of
                                   get_quantized_obs_from_ordinal (quantization_model_log.py:43-51) under the cost
                                   norm(Wx*(T_hat - Obs))**2 of qmc_dowjons.ipynb c1:112,130.  noise_std is not
                                   used; nll_out receives the cost.  Observed-entry kernels only. */
+  QMC_EPI_LOGISTIC = 1u << 6   /* logistic instead of Gaussian noise: P = F((hi - x)/s) - F((lo - x)/s) with
+                                  F = F_sigmoid (quantization_model.py:43-47) and s = noise_std (s = 1 is the
+                                  reference's F_sigmoid as it stands), evaluated as a stable log-difference.
+                                  Observed-entry kernels only. */
 };
 
 /*

@@ -246,6 +246,50 @@ def lsq_and_grads_fp64(S, C, Y, Wx, bin_boundaries, offset=None):
     return float(np.sum(d * d)), (C64 @ gT).reshape(S64.shape), Smat @ gT.T
 
 
+# ----------------------------------------------------------------------------------------
+# logistic noise model: prob_probit with F_sigmoid in place of F_probit
+# ----------------------------------------------------------------------------------------
+def prob_sigmoid(Y, X_hat, bin_boundaries, scale=1.0, sentinels=True):
+    """``P = F_sigmoid((U - X)/s) - F_sigmoid((W - X)/s)``: the body of prob_probit
+    (quantization_model.py:31-38) with the reference's logistic CDF (F_sigmoid, :43-47) in place of
+    F_probit.  The reference ships F_sigmoid (and uses it in NegLikelihood(probit=False), :107-110) but no
+    multi-level logistic function, so this composition is pinned through F_sigmoid's golden vectors only."""
+    bb = effective_boundaries(bin_boundaries, sentinels)
+    return F_sigmoid((bb[Y + 1] - X_hat) / scale) - F_sigmoid((bb[Y] - X_hat) / scale)
+
+
+def logistic_nll_and_grads_fp64(S, C, Y, Wx, bin_boundaries, scale=1.0, offset=None, sentinels=True):
+    """float64 masked NLL of the logistic model and analytic gradients, observed entries only, written
+    without cancellation: log P = log(-expm1(-(zu-zl))) - softplus(-zu) - softplus(zl)."""
+    S64 = np.asarray(S.detach().cpu().numpy(), dtype=np.float64)
+    C64 = np.asarray(C.detach().cpu().numpy(), dtype=np.float64)
+    R, K = C64.shape
+    Smat = S64.reshape(R, -1)
+    Yk = np.asarray(Y.detach().cpu().numpy()).reshape(K, -1)
+    obs = np.asarray(Wx.detach().cpu().numpy()).reshape(K, -1) != 0
+    bb = np.asarray(bin_boundaries.detach().cpu().numpy(), dtype=np.float64).copy()
+    if sentinels:
+        bb[0], bb[-1] = -REF_SENTINEL, REF_SENTINEL
+    s = float(np.float32(scale))
+    T = C64.T @ Smat
+    X = np.log(T + float(offset)) if offset is not None else T
+    zu, zl = (bb[Yk + 1] - X) / s, (bb[Yk] - X) / s
+
+    def softplus(t):
+        return np.maximum(t, 0.0) + np.log1p(np.exp(-np.abs(t)))
+
+    def sigmoid(t):
+        e = np.exp(-np.abs(t))
+        return np.where(t >= 0, 1.0 / (1.0 + e), e / (1.0 + e))
+
+    with np.errstate(all="ignore"):
+        logP = np.log(-np.expm1(-(zu - zl))) - softplus(-zu) - softplus(zl)
+        gX = np.where(obs, (sigmoid(-zu) - sigmoid(zl)) / s, 0.0)
+    nll = -float(np.sum(logP[obs]))
+    gT = gX / (T + float(offset)) if offset is not None else gX
+    return nll, (C64 @ gT).reshape(S64.shape), Smat @ gT.T
+
+
 def stable_logP_fp64(zl: np.ndarray, zu: np.ndarray):
     """float64 log P and (exp(-zu^2) - exp(-zl^2)) / P for P = 0.5*(erf(zu) - erf(zl)), zl < zu,
     evaluated without cancellation or underflow: both bounds in the right tail -> scaled

@@ -19,6 +19,7 @@ QMC_FORWARD_ONLY = 1 << 2
 QMC_SKIP_GS = 1 << 3
 QMC_SKIP_GC = 1 << 4
 QMC_EPI_LSQ = 1 << 5
+QMC_EPI_LOGISTIC = 1 << 6
 QMC_ALGO_AUTO, QMC_ALGO_FLAT, QMC_ALGO_TILED, QMC_ALGO_LANES = 0, 1, 2, 3
 
 

@@ -159,6 +159,25 @@ __device__ __forceinline__ BinEval probit_one_sided_fast(float thr, float m, flo
   return o;
 }
 
+// Logistic bin (F = F_sigmoid, quantization_model.py:43-47): with zl = (lo-x)/s < zu = (hi-x)/s,
+//   P = F(zu) - F(zl) = (1 - e^{-(zu-zl)}) * F(zu) * F(-zl)
+//   log P = log(-expm1(-(zu-zl))) - softplus(-zu) - softplus(zl)       (no cancellation, no overflow)
+//   d(-log P)/dx = (F(-zu) - F(zl)) / s                                (the first term does not depend on x)
+__device__ __forceinline__ float softplus_f(float t) { return fmaxf(t, 0.0f) + log1pf(expf(-fabsf(t))); }
+__device__ __forceinline__ float sigmoid_f(float t) {
+  const float e = expf(-fabsf(t));
+  const float r = 1.0f / (1.0f + e);
+  return t >= 0.0f ? r : e * r;
+}
+__device__ __forceinline__ BinEval logistic_bin(float lo, float hi, float x, float inv_s) {
+  const float zl = (lo - x) * inv_s, zu = (hi - x) * inv_s;
+  const float width = (hi - lo) * inv_s;  // = zu - zl without the rounding of the two differences
+  BinEval o;
+  o.logp = logf(-expm1f(-width)) - softplus_f(-zu) - softplus_f(zl);
+  o.gx = (sigmoid_f(-zu) - sigmoid_f(zl)) * inv_s;
+  return o;
+}
+
 // The reference's own arithmetic, literally: F = 0.5*(1+erf(z)), P = F(zu) - F(zl), log P, and
 // the gradient autograd derives from it.  Underflows to P == 0 (log -> -inf, gradient -> inf/NaN)
 // where the reference does.

@@ -494,6 +494,8 @@ extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, con
   if (R > DT_RP) return set_error(QMC_ERR_UNSUPPORTED, "dense path needs rank <= %d (got %d)", DT_RP, R);
   QMC_REQUIRE(lik->n_bounds >= 2 && lik->n_bounds <= QMC_MAX_BOUNDS - 1, "n_bounds %d out of range (255 is the 'unobserved' code)", lik->n_bounds);
   QMC_REQUIRE(lik->noise_std > 0.0f, "noise_std must be positive");
+  if (lik->flags & QMC_EPI_LOGISTIC)
+    return set_error(QMC_ERR_UNSUPPORTED, "QMC_EPI_LOGISTIC: the logistic model runs on the observed-entry kernels only");
   if (lik->flags & QMC_EPI_LSQ)
     return set_error(QMC_ERR_UNSUPPORTED, "QMC_EPI_LSQ: the least-squares baseline runs on the observed-entry kernels only");
   const bool grad = !(lik->flags & QMC_FORWARD_ONLY);

@@ -95,7 +95,9 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
   while ((1LL << l) < IJ) ++l;
   prm.div_magic = (uint32_t)(((1ULL << (31 + l)) / (uint64_t)IJ) + 1ULL);
   prm.div_shift = l - 1;
-  const float a = (lik->flags & QMC_EPI_LSQ) ? 1.0f : probit_scale(lik->noise_std);  // least squares has no noise model
+  const float a = (lik->flags & QMC_EPI_LSQ) ? 1.0f                   // least squares has no noise model
+                  : (lik->flags & QMC_EPI_LOGISTIC) ? lik->noise_std  // logistic scale, no sqrt(2)
+                                                    : probit_scale(lik->noise_std);
   prm.inv_a = 1.0f / a;
   prm.offset = lik->offset;
   for (int i = 0; i < lik->n_bounds; ++i) prm.bounds[i] = lik->bounds[i];
@@ -104,6 +106,7 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
   // epilogue: reference-literal, one-bit fast path (both outer bounds numerically infinite), or general
   int epi = EPI_STABLE;
   if (lik->flags & QMC_EPI_LSQ) epi = EPI_LSQ;
+  else if (lik->flags & QMC_EPI_LOGISTIC) epi = EPI_LOGISTIC;
   else if (lik->flags & QMC_EPI_REFERENCE) epi = EPI_REFERENCE;
   else if (lik->n_bounds == 3) {
     // erfc(z) == 0 exactly (even in double) for z > 27; require the sentinel to sit that far out for

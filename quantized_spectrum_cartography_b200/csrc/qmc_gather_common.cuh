@@ -44,7 +44,7 @@ struct GatherParams {
   float bounds[QMC_MAX_BOUNDS];
 };
 
-enum : int { EPI_STABLE = 0, EPI_REFERENCE = 1, EPI_ONEBIT = 2, EPI_LSQ = 3 };
+enum : int { EPI_STABLE = 0, EPI_REFERENCE = 1, EPI_ONEBIT = 2, EPI_LSQ = 3, EPI_LOGISTIC = 4 };
 
 __device__ __forceinline__ int fast_div(uint32_t n, uint32_t magic, int shift) {
   return (int)(__umulhi(n, magic) >> shift);
@@ -67,6 +67,8 @@ __device__ __forceinline__ BinEval eval_entry(const GatherParams& prm, float t, 
     o.logp = -d * d;
     o.gx = 2.0f * d;
     return o;
+  } else if (EPI == EPI_LOGISTIC) {
+    return logistic_bin(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
   } else if (EPI == EPI_ONEBIT) {
     return probit_one_sided_fast(prm.thr, lvl ? -prm.inv_a : prm.inv_a, x);
   } else if (EPI == EPI_REFERENCE) {
@@ -183,6 +185,10 @@ template <int RP> int launch_lanes_rp(const GatherParams& prm, int epi, bool log
       case EPI_REFERENCE:                                                            \
         if (logd) { if (grad) GO(EPI_REFERENCE, true, true); else GO(EPI_REFERENCE, true, false); }    \
         else { if (grad) GO(EPI_REFERENCE, false, true); else GO(EPI_REFERENCE, false, false); }       \
+        break;                                                                       \
+      case EPI_LOGISTIC:                                                             \
+        if (logd) { if (grad) GO(EPI_LOGISTIC, true, true); else GO(EPI_LOGISTIC, true, false); }      \
+        else { if (grad) GO(EPI_LOGISTIC, false, true); else GO(EPI_LOGISTIC, false, false); }         \
         break;                                                                       \
       case EPI_LSQ:                                                                  \
         if (logd) { if (grad) GO(EPI_LSQ, true, true); else GO(EPI_LSQ, true, false); }                \

@@ -37,7 +37,7 @@ def _as_float(v) -> float:
 
 def make_likelihood(bin_boundaries, noise_std, *, offset=None, log_domain: Optional[bool] = None,
                     sentinels: Optional[bool] = None, reference_epilogue: bool = False,
-                    forward_only: bool = False, least_squares: bool = False) -> Likelihood:
+                    forward_only: bool = False, least_squares: bool = False, model: str = "probit") -> Likelihood:
     """Pack the model the way the reference's two files define it.
 
     ``offset is None`` -> linear-domain file: no log link, outer boundaries replaced by -/+1e5
@@ -45,10 +45,18 @@ def make_likelihood(bin_boundaries, noise_std, *, offset=None, log_domain: Optio
     boundaries used as they are (quantization_model_log.py:32-34).  ``log_domain`` / ``sentinels``
     override either default.  The caller's table is never modified (the reference clones it).
 
+    ``model="logistic"`` replaces the Gaussian CDF F_probit by the logistic CDF F_sigmoid
+    (quantization_model.py:43-47) in ``P = F(U - x) - F(W - x)``; ``noise_std`` is then the logistic scale
+    (1 = F_sigmoid as the reference writes it).
+
     ``least_squares=True`` selects the masked least-squares baseline on the bin mid-points instead of
     the likelihood (qmc_dowjons.ipynb c1:112; quantization_model_log.py:43-51): ``noise_std`` is not
     used and the table is taken as it is (the reference's mid-point function never substitutes
     sentinels) unless ``sentinels=True`` is passed explicitly."""
+    if model not in ("probit", "logistic"):
+        raise ValueError(f"model must be 'probit' or 'logistic', got {model!r}")
+    if model == "logistic" and (least_squares or reference_epilogue):
+        raise ValueError("model='logistic' cannot be combined with least_squares / reference_epilogue")
     bb = torch.as_tensor(bin_boundaries, dtype=torch.float32).detach().cpu().reshape(-1).clone()
     n = bb.numel()
     if not 2 <= n <= _lib.QMC_MAX_BOUNDS:
@@ -62,7 +70,8 @@ def make_likelihood(bin_boundaries, noise_std, *, offset=None, log_domain: Optio
     lik = Likelihood()
     lik.n_bounds = n
     lik.flags = ((_lib.QMC_LOG_DOMAIN if log_domain else 0) | (_lib.QMC_EPI_REFERENCE if reference_epilogue else 0)
-                 | (_lib.QMC_FORWARD_ONLY if forward_only else 0) | (_lib.QMC_EPI_LSQ if least_squares else 0))
+                 | (_lib.QMC_FORWARD_ONLY if forward_only else 0) | (_lib.QMC_EPI_LSQ if least_squares else 0)
+                 | (_lib.QMC_EPI_LOGISTIC if model == "logistic" else 0))
     lik.noise_std = 1.0 if least_squares and noise_std is None else _as_float(noise_std)
     lik.offset = 0.0 if offset is None else _as_float(offset)
     for i, v in enumerate(bb.tolist()):
@@ -179,7 +188,7 @@ def _cached_obs(Y: torch.Tensor, Wx: Optional[torch.Tensor], K: int, IJ: int, de
 
 
 def qmc_nll(S, C_, Y, Wx, bin_boundaries, noise_std, offset=None, log_domain=None, sentinels=None,
-            reference_epilogue=False, obs: Optional[ObsSet] = None, device=None) -> torch.Tensor:
+            reference_epilogue=False, obs: Optional[ObsSet] = None, device=None, model: str = "probit") -> torch.Tensor:
     """Drop-in for the reference idiom (module docstring).  Shapes and dtypes are the reference's:
     ``S [R,1,I,J]`` (or ``[R,I,J]``), ``C [R,K]``, ``Y`` int64 ``[K,1,I,J]``, ``Wx`` 0/1 float of
     the same shape, ``bin_boundaries`` 1-D (not modified), ``noise_std``/``offset`` floats or
@@ -192,7 +201,7 @@ def qmc_nll(S, C_, Y, Wx, bin_boundaries, noise_std, offset=None, log_domain=Non
     S3 = S.reshape(1, R, -1)
     IJ = S3.shape[2]
     lik = make_likelihood(bin_boundaries, noise_std, offset=offset, log_domain=log_domain, sentinels=sentinels,
-                          reference_epilogue=reference_epilogue)
+                          reference_epilogue=reference_epilogue, model=model)
     if obs is None:
         obs = _cached_obs(Y, Wx, K, IJ, dev, R)
     S3d = S3.to(device=dev, dtype=torch.float32)

@@ -45,7 +45,7 @@ def test_python_flag_constants_mirror_the_header():
     from quantized_spectrum_cartography_b200 import _lib
     text = open(HEADER).read()
     flags = dict(re.findall(r"\b(QMC_(?:LOG_DOMAIN|EPI_\w+|FORWARD_ONLY|SKIP_\w+))\s*=\s*1u\s*<<\s*(\d+)", text))
-    assert {"QMC_LOG_DOMAIN", "QMC_EPI_REFERENCE", "QMC_FORWARD_ONLY", "QMC_SKIP_GS", "QMC_SKIP_GC", "QMC_EPI_LSQ"} <= set(flags)
+    assert {"QMC_LOG_DOMAIN", "QMC_EPI_REFERENCE", "QMC_FORWARD_ONLY", "QMC_SKIP_GS", "QMC_SKIP_GC", "QMC_EPI_LSQ", "QMC_EPI_LOGISTIC"} <= set(flags)
     for name, shift in flags.items():
         assert getattr(_lib, name) == 1 << int(shift), name
     assert len(set(flags.values())) == len(flags)

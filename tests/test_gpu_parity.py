@@ -829,3 +829,46 @@ def test_least_squares_solver_matches_torch_loop(q):
                     par.clamp_(min=0)
         assert rel_err(got.S[b].cpu().numpy(), Sb.detach().reshape(R, -1).numpy()) < 1e-4
         assert rel_err(got.C[b].cpu().numpy(), Cb.detach().numpy()) < 1e-4
+
+
+# ---- logistic noise model (BASELINE north star: "Gaussian/logistic CDF difference") ---------------------
+@pytest.mark.parametrize("R,levels,log_domain,sentinels", [(4, 2, False, True), (8, 8, True, False), (3, 5, False, True), (16, 16, True, True)])
+@pytest.mark.parametrize("algo", ["flat", "tiled", "lanes"])
+def test_logistic_model_all_kernels(q, R, levels, log_domain, sentinels, algo):
+    """QMC_EPI_LOGISTIC in every observed-entry kernel against the tail-stable float64 statement of
+    P = F_sigmoid((U-x)/s) - F_sigmoid((W-x)/s): NLL 1e-5, gradients 1e-4; the dense path refuses the flag."""
+    from quantized_spectrum_cartography_b200 import _lib, dense
+    B, I, J, K = 4, 17, 13, 32
+    S, C, Y, Wx, bb, sigma, off = _random_instance(B, I, J, K, R, 0.3, levels, seed=11 * R + levels, log_domain=log_domain)
+    Wx[1] = 0
+    Wx[2, :, : (I * J) // 2] = 0
+    scale = 0.6 * sigma
+    lik = q.make_likelihood(bb, scale, offset=off, sentinels=sentinels, model="logistic")
+    assert lik.flags & _lib.QMC_EPI_LOGISTIC
+    IJ = I * J
+    if algo == "flat":
+        obs, a = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, B), _lib.QMC_ALGO_FLAT
+    elif algo == "tiled":
+        obs = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, B, n_sub=4, sub_pixels=-(-IJ // 4), tile_warps=2, bank_mod=q.bank_mod_for_rank(R))
+        a = _lib.QMC_ALGO_TILED
+    else:
+        obs = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, B, n_sub=4, sub_pixels=-(-IJ // 4), tile_warps=4, lanes=True)
+        a = _lib.QMC_ALGO_LANES
+    nll, gS, gC = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik, algo=a)
+    for b in range(B):
+        want = oc.logistic_nll_and_grads_fp64(S[b].reshape(R, 1, I, J), C[b], Y[b].reshape(K, 1, I, J),
+                                              Wx[b].reshape(K, 1, I, J), bb, scale, off, sentinels)
+        assert nll[b].item() == pytest.approx(want[0], rel=NLL_RTOL, abs=1e-12)
+        if Wx[b].sum() == 0:
+            assert gS[b].abs().max() == 0 and gC[b].abs().max() == 0
+            continue
+        assert rel_err(gS[b].cpu().numpy(), want[1].reshape(R, -1)) < GRAD_RTOL
+        assert rel_err(gC[b].cpu().numpy(), want[2]) < GRAD_RTOL
+    if algo == "flat" and R == 4:
+        # the drop-in call and the refusal of the dense kernel
+        Sg = S[0].reshape(R, 1, I, J).cuda().requires_grad_(True)
+        v = q.qmc_nll(Sg, C[0].cuda(), Y[0].reshape(K, 1, I, J), Wx[0].reshape(K, 1, I, J), bb, scale, model="logistic")
+        assert v.item() == pytest.approx(nll[0].item(), rel=1e-6)
+        dobs = dense.pack_dense(Y[0].cuda(), Wx[0].cuda(), K)
+        with pytest.raises(_lib.QmcError, match="logistic"):
+            dense.nll_fwd_bwd_dense(S[0].cuda(), C[0].cuda(), dobs, lik)

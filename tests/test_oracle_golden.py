@@ -131,3 +131,31 @@ def test_least_squares_baseline_matches_reference(name, fixture_instance):
     # the vectorised statement gives the same cost
     cost_v = oc.masked_lsq(c["S"], c["C"], c["Y"], c["Wx"], c["bb"], c["offset"], vectorised=True)
     assert abs(cost_v.item() - c["cost"]) <= 1e-6 * abs(c["cost"])
+
+
+@pytest.mark.parametrize("sentinels", [False, True])
+def test_logistic_model_fp64_statement_matches_the_composition(sentinels):
+    """prob_sigmoid = the body of prob_probit with the reference's F_sigmoid; its tail-stable float64 statement
+    (what the CUDA logistic epilogue is checked against) agrees with autograd through the literal composition.
+    With the +-1e5 sentinels the literal form overflows exp() in the backward pass (NaN), like the probit
+    tails: there only the NLL is compared."""
+    g = torch.Generator().manual_seed(5)
+    R, K, I, J = 3, 6, 5, 4
+    S = (torch.rand(R, 1, I, J, generator=g) * 0.1 + 0.01).double()
+    C = (torch.rand(R, K, generator=g) * 0.2 + 0.02).double()
+    T = oc.get_tensor_vectorised(S.float(), C.float())
+    bb = torch.linspace(T.min().item(), T.max().item(), 5)
+    Y = oc.assign_levels(T + 0.002 * torch.randn(T.shape, generator=g), bb).reshape(K, 1, I, J)
+    Wx = torch.bernoulli(torch.full((K, 1, I, J), 0.5), generator=g)
+    scale = float(np.float32(0.003))
+    Sd, Cd = S.clone().requires_grad_(True), C.clone().requires_grad_(True)
+    Th = torch.einsum("rij,rk->kij", Sd[:, 0], Cd).unsqueeze(1)
+    nll = -(Wx.double() * torch.log(oc.prob_sigmoid(Y, Th, bb.double(), scale, sentinels=sentinels))).sum()
+    nll.backward()
+    want = oc.logistic_nll_and_grads_fp64(S, C, Y, Wx, bb, scale, None, sentinels)
+    assert nll.item() == pytest.approx(want[0], rel=1e-12)
+    if not sentinels:
+        np.testing.assert_allclose(Sd.grad.numpy(), want[1], rtol=1e-9, atol=1e-12 * np.abs(want[1]).max())
+        np.testing.assert_allclose(Cd.grad.numpy(), want[2], rtol=1e-9, atol=1e-12 * np.abs(want[2]).max())
+    else:
+        assert np.isfinite(want[1]).all() and np.isfinite(want[2]).all()
