@@ -187,3 +187,43 @@ def test_cfg2_instance_vs_oracle_subsample(q):
     assert abs(nll[0].item() / want[0] - 1) < 1e-5
     assert np.linalg.norm(gS[0].cpu().numpy() - want[1].reshape(R, -1)) / np.linalg.norm(want[1]) < 1e-4
     assert np.linalg.norm(gC[0].cpu().numpy() - want[2]) / np.linalg.norm(want[2]) < 1e-4
+
+
+@pytest.mark.parametrize("epilogue", ["lsq", "logistic"])
+def test_cfg3_full_batch_other_epilogues(q, epilogue):
+    """cfg3 at full size with the least-squares and the logistic epilogue: lane-stream kernel against the
+    tiled kernel on all 4096 maps, additivity over a mask split, and sampled maps against the float64 oracle."""
+    from quantized_spectrum_cartography_b200 import _lib
+    B, I, J, K, R = 4096, 51, 51, 64, 4
+    IJ = I * J
+    maps, Y, Wx, bb, sigma = _one_bit_problem(q, B, I, J, K, R, 0.10, seed=1)
+    if epilogue == "lsq":
+        lik = q.make_likelihood(bb, None, least_squares=True)
+    else:
+        lik = q.make_likelihood(bb, 0.5 * sigma, model="logistic")
+    S, C = (0.8 * maps.S_true).contiguous(), maps.C_true.contiguous()
+    S_pm = S.transpose(1, 2).contiguous().transpose(1, 2)
+    build = lambda y, w: q.make_obs(y, w, K, y.device, B=y.shape[0], R=R, tiled=True, lanes=True)
+    obs = build(Y, Wx)
+    assert obs.lanes
+    nll, gS, gC = q.nll_fwd_bwd(S_pm, C, obs, lik)
+    assert torch.isfinite(nll).all() and torch.isfinite(gS).all() and torch.isfinite(gC).all()
+    n_sub, sub, tw = q.plan_tiles(IJ, K, R)
+    obs_t = q.build_obs(Y, Wx, K, IJ, B, n_sub=n_sub, sub_pixels=sub, tile_warps=tw, bank_mod=q.bank_mod_for_rank(R))
+    t = q.nll_fwd_bwd(S, C, obs_t, lik, algo=_lib.QMC_ALGO_TILED)
+    assert ((nll - t[0]).abs() / t[0].abs()).max().item() < 1e-6
+    assert ((gS - t[1]).flatten(1).norm(dim=1) / t[1].flatten(1).norm(dim=1)).max().item() < 1e-5
+    assert ((gC - t[2]).flatten(1).norm(dim=1) / t[2].flatten(1).norm(dim=1)).max().item() < 1e-5
+    # additivity over a split of the mask
+    half = (torch.rand(Wx.shape, device=Wx.device, generator=torch.Generator(device=Wx.device).manual_seed(5)) < 0.5).float()
+    a = q.nll_fwd_bwd(S_pm, C, build(Y, Wx * half), lik)
+    b = q.nll_fwd_bwd(S_pm, C, build(Y, Wx * (1 - half)), lik)
+    assert ((a[0] + b[0] - nll).abs() / nll.abs()).max().item() < 1e-6   # fp32 partial sums per lane
+    assert rel(a[1] + b[1], gS) < 1e-5 and rel(a[2] + b[2], gC) < 1e-5
+    # sampled maps against the float64 oracle
+    for m in (0, 1777, 4095):
+        args = (S[m].cpu().reshape(R, 1, I, J), C[m].cpu(), Y[m].cpu().long().reshape(K, 1, I, J), Wx[m].cpu().reshape(K, 1, I, J), bb)
+        want = oc.lsq_and_grads_fp64(*args) if epilogue == "lsq" else oc.logistic_nll_and_grads_fp64(*args, 0.5 * sigma, None, True)
+        assert nll[m].item() == pytest.approx(want[0], rel=1e-5)
+        assert rel(gS[m].cpu(), torch.from_numpy(want[1].reshape(R, -1))) < 1e-4
+        assert rel(gC[m].cpu(), torch.from_numpy(want[2])) < 1e-4
