@@ -142,7 +142,9 @@ def main():
         R = C.shape[1]
         alg = obs.nobs * 5 + B * (2 * 4 * R * (S.shape[2] + C.shape[2]) + 4)
         lik_lsq = q.make_likelihood(pb["bb"], None, least_squares=True)
-        for name, lk in (("likelihood (one-bit probit)", pb["lik"]), ("least squares on bin mid-points", lik_lsq)):
+        lik_logit = q.make_likelihood(pb["bb"], 0.5 * pb["sigma"], model="logistic")
+        for name, lk in (("likelihood (one-bit probit)", pb["lik"]), ("least squares on bin mid-points", lik_lsq),
+                         ("likelihood (logistic, stable log-difference)", lik_logit)):
             t = timeit(lambda: q.nll_fwd_bwd(S, C, obs, lk))
             print(json.dumps({"case": f"cfg3 x {B}", "epilogue": name, "layout": "lanes" if obs.lanes else "rows",
                               "nobs": obs.nobs, "ms": t, "entries_per_s": obs.nobs / (t * 1e-3),
