@@ -142,7 +142,7 @@ def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_bud
                                   torch.cuda.current_stream().cuda_stream))
     del noisy
     Wx = torch.bernoulli(torch.full(T.shape, c["sampling"], device=device), generator=gen)
-    n_sub, sub, tw = q.plan_tiles(IJ, K, R, tile_warps, smem_budget_kb * 1024, lanes=lanes)
+    n_sub, sub, tw = q.plan_tiles(IJ, K, R, tile_warps, smem_budget_kb * 1024, lanes=lanes, max_level=c["levels"] - 1)
     obs = q.build_obs(Y, Wx, K, IJ, n_maps, n_sub=n_sub, sub_pixels=sub, tile_warps=tw,
                       bank_mod=0 if lanes else (bank_mod if bank_mod >= 0 else q.bank_mod_for_rank(R)), lanes=lanes)
     lik = q.make_likelihood(bb, sigma)

@@ -37,7 +37,7 @@ extern "C" {
 #define QMC_API
 #endif
 
-#define QMC_ABI_VERSION 2
+#define QMC_ABI_VERSION 3
 #define QMC_MAX_BOUNDS 257 /* uint8 levels: at most 256 levels = 257 boundaries (qmc/utils.py:24) */
 #define QMC_MAX_RANK 32
 
@@ -102,17 +102,27 @@ typedef struct qmc_obs_view {
   int32_t n_sub;       /* pixel sub-tiles per map */
   int32_t sub_pixels;  /* pixels per sub-tile */
   /* Lane-stream layout (qmc_obs_build_lanes), NULL otherwise: the entries of every (map, sub-tile)
-   * stream re-cut so that each lane of the owning warp walks one band at a time and the 32 entries
-   * of a step hit 32 different pixels; a lane changes band only at a multiple of four steps.
-   * word: bit 31 = level & 1, bits 24..30 = level >> 1, bits 15..23 = band, bits 0..14 = tile-local
-   * pixel; level 0xFF (bits 24..31 all set) marks padding.  Steps are stored in groups of four,
-   * lane-interleaved: word(t, lane) at stream_off[s] + ((t / 4) * 32 + lane) * 4 + t % 4.
+   * stream re-cut so that each lane of the owning warp walks a list of runs -- a band and a number of
+   * 4-step groups -- and the 32 entries of a step hit 32 different pixels; a lane changes band only at a
+   * multiple of four steps.  A stream starts with its run table, n_runs entries per lane stored
+   * [entry][lane]: bits 0..8 = row of the warp's gC copy the run's partial goes to (the band, or K+1+lane for
+   * a piece that continues a band begun by another lane), bits 9..17 = band (K = none), bits 18..31 = groups
+   * (the last entry of a lane never ends).  The words follow in 512-byte slots of 32 lanes x 16 bytes:
+   *   word_bits == 32: one group per slot; bit 31 = level & 1, bits 24..30 = level >> 1, bits 0..14 = tile-local
+   *                    pixel; level 0xFF (bits 24..31 all set) marks padding;
+   *   word_bits == 16: two groups per slot (halfwords 0..3 and 4..7 of a lane's 16 bytes); the top lvl_bits bits
+   *                    = level, the next bit = padding flag (padding also has all level bits set), the rest =
+   *                    tile-local pixel.
    * idx/lvl/row_off are not used by the kernel. */
   const uint32_t* words_dev;
-  const int64_t* stream_off_dev; /* B*n_sub + 1 word offsets, multiples of 128 */
+  const int64_t* stream_off_dev; /* B*n_sub + 1 offsets in 32-bit words, multiples of 32 */
   const int32_t* nrows_dev;      /* B*n_sub steps per stream, multiples of 4 */
-  int64_t stream_stride;         /* > 0: stream s starts at word s * stream_stride (a multiple of 128) and
+  int64_t stream_stride;         /* > 0: stream s starts at word s * stream_stride (a multiple of 32) and
                                     stream_off_dev is not read -- lets a CTA prefetch a later CTA's data */
+  int32_t n_runs;                /* run-table entries per lane */
+  int32_t word_bits;             /* 16 or 32 */
+  int32_t lvl_bits;              /* word_bits == 16: width of the level field */
+  int32_t has_cont;              /* != 0: continuation rows are in use (bands split over lanes) */
 } qmc_obs_view_t;
 
 QMC_API int qmc_abi_version(void);
@@ -162,9 +172,9 @@ QMC_API int qmc_obs_fill(const void* y_dev, int y_is_int64, const float* wx_dev,
 QMC_API int qmc_obs_build_lanes(int32_t* idx_rows_dev, uint8_t* lvl_rows_dev, const int64_t* row_off_dev,
                         int B, int K, int IJ, int n_sub, int sub_pixels, int tile_warps,
                         const int64_t* stream_off_dev, uint32_t* words_out_dev, int32_t* nrows_out_dev,
-                        int32_t* overflow_dev, void* stream);
+                        int32_t* overflow_dev, int n_runs, int word_bits, int lvl_bits, void* stream);
 /* Shared-memory bytes of the lanes kernel for a geometry (0 if it cannot run it). */
-QMC_API int64_t qmc_lanes_smem_bytes(int K, int R, int sub_pixels, int tile_warps);
+QMC_API int64_t qmc_lanes_smem_bytes(int K, int R, int sub_pixels, int tile_warps, int n_runs, int word_bits);
 
 /* ---- a2..a7: fused masked low-rank reconstruction + quantized NLL + factor gradients ---------- */
 

@@ -34,7 +34,8 @@ class ObsView(C.Structure):
     _fields_ = [("idx_dev", C.c_void_p), ("lvl_dev", C.c_void_p), ("row_off_dev", C.c_void_p),
                 ("n_sub", C.c_int32), ("sub_pixels", C.c_int32),
                 ("words_dev", C.c_void_p), ("stream_off_dev", C.c_void_p), ("nrows_dev", C.c_void_p),
-                ("stream_stride", C.c_int64)]
+                ("stream_stride", C.c_int64), ("n_runs", C.c_int32), ("word_bits", C.c_int32),
+                ("lvl_bits", C.c_int32), ("has_cont", C.c_int32)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -49,8 +50,8 @@ SIGNATURES = {
     "qmc_obs_scan_ws_elems": (_L, [_L]),
     "qmc_obs_count_scan": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "qmc_obs_fill": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "qmc_obs_build_lanes": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "qmc_lanes_smem_bytes": (_L, [_I, _I, _I, _I]),
+    "qmc_obs_build_lanes": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "qmc_lanes_smem_bytes": (_L, [_I, _I, _I, _I, _I, _I]),
     "qmc_sumsq_per_map": (_I, [_P, _I, _L, _P, _P]),
     "qmc_adam_frob_project": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _F, _F, _F, _F, _F, _I, _I, _P, _P]),
     "qmc_counter_add": (_I, [_P, _I, _P]),

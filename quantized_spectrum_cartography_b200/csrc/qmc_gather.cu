@@ -16,11 +16,11 @@
 
 using namespace qmc;
 
-extern "C" int64_t qmc_lanes_smem_bytes(int K, int R, int sub_pixels, int tile_warps) {
-  if (K <= 0 || R <= 0 || R > QMC_MAX_RANK || sub_pixels <= 0 || tile_warps <= 0 || tile_warps > 8) return 0;
+extern "C" int64_t qmc_lanes_smem_bytes(int K, int R, int sub_pixels, int tile_warps, int n_runs, int word_bits) {
+  if (K <= 0 || R <= 0 || R > QMC_MAX_RANK || sub_pixels <= 0 || tile_warps <= 0 || tile_warps > 8 || n_runs <= 0) return 0;
   int RP = 1;
   while (RP < R) RP <<= 1;
-  const size_t b = lanes_smem_bytes(K, RP, sub_pixels, tile_warps, true);
+  const size_t b = lanes_smem_bytes(K, RP, sub_pixels, tile_warps, true, n_runs, word_bits == 16);
   return b <= 227 * 1024 ? (int64_t)b : 0;
 }
 
@@ -73,6 +73,10 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
   prm.C = C_dev; prm.idx = obs->idx_dev; prm.lvl = obs->lvl_dev; prm.row_off = obs->row_off_dev;
   prm.words = obs->words_dev; prm.stream_off = obs->stream_off_dev; prm.nrows = obs->nrows_dev;
   prm.stream_stride = lanes ? obs->stream_stride : 0;
+  prm.n_runs = lanes ? obs->n_runs : 0;
+  prm.word16 = lanes && obs->word_bits == 16;
+  prm.lvl_bits = lanes ? obs->lvl_bits : 0;
+  prm.has_cont = lanes ? obs->has_cont : 0;
   prm.lookahead = 0;
   prm.want_gs = want_gs; prm.want_gc = want_gc;
   prm.fuse_update = fu != nullptr;
@@ -124,6 +128,14 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
   if (lanes) {
     QMC_REQUIRE(algo == QMC_ALGO_AUTO || algo == QMC_ALGO_LANES, "a lane-stream observation set needs QMC_ALGO_LANES");
     QMC_REQUIRE(K <= 256 && lik->n_bounds <= 256, "lane-stream layout: K <= 256 and at most 255 levels");
+    QMC_REQUIRE(obs->n_runs >= 1 && obs->n_runs <= 64 && (obs->word_bits == 16 || obs->word_bits == 32),
+                "lane-stream layout: n_runs %d / word_bits %d out of range", obs->n_runs, obs->word_bits);
+    QMC_REQUIRE(obs->word_bits == 32 || (obs->lvl_bits >= 1 && obs->lvl_bits <= 8 &&
+                                         (int64_t)obs->sub_pixels * tile_warps <= (1LL << (15 - obs->lvl_bits))),
+                "lane-stream layout: 16-bit words cannot hold %d level bits and a tile of %lld pixels", obs->lvl_bits,
+                (long long)obs->sub_pixels * tile_warps);
+    QMC_REQUIRE(obs->word_bits == 32 || epi != EPI_ONEBIT || obs->lvl_bits == 1,
+                "lane-stream layout: a one-bit model needs observation words with a 1-bit level field");
     algo = QMC_ALGO_LANES;
   } else {
     QMC_REQUIRE(algo != QMC_ALGO_LANES, "QMC_ALGO_LANES needs a lane-stream observation set (qmc_obs_build_lanes)");
@@ -136,7 +148,7 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
   if (algo == QMC_ALGO_LANES) {
     QMC_REQUIRE(tile_warps > 0 && tile_warps <= 8, "tile_warps %d out of range [1, 8]", tile_warps);
     QMC_REQUIRE(obs->n_sub % tile_warps == 0, "n_sub %d is not a multiple of tile_warps %d", obs->n_sub, tile_warps);
-    QMC_REQUIRE(lanes_smem_bytes(K, RP, obs->sub_pixels, tile_warps, grad) <= 227 * 1024,
+    QMC_REQUIRE(lanes_smem_bytes(K, RP, obs->sub_pixels, tile_warps, grad, obs->n_runs, obs->word_bits == 16) <= 227 * 1024,
                 "tile of %d pixels x rank %d (+ %d private gC copies) does not fit shared memory",
                 obs->sub_pixels * tile_warps, RP, tile_warps);
     prm.tile_warps = tile_warps;
@@ -145,7 +157,7 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
       int dev = 0, sms = 0;
       QMC_CUDA_CHECK(cudaGetDevice(&dev));
       QMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      const size_t per_cta = lanes_smem_bytes(K, RP, obs->sub_pixels, tile_warps, grad) + 1024 + 256;
+      const size_t per_cta = lanes_smem_bytes(K, RP, obs->sub_pixels, tile_warps, grad, obs->n_runs, obs->word_bits == 16) + 1024 + 256;
       int per_sm = (int)((228 * 1024) / per_cta);
       per_sm = per_sm < 1 ? 1 : per_sm;
       const int by_threads = 2048 / (tile_warps * 32), by_regs = 65536 / (128 * tile_warps * 32);
@@ -215,14 +227,16 @@ extern "C" int qmc_solver_s_step_fused(float* S_dev, int64_t s_stride_b, int64_t
   QMC_REQUIRE(lam == 0.0f || sumsq_in_dev, "the Frobenius regulariser needs the squared norms of S");
   QMC_REQUIRE(step >= 0 && (step > 0 || step_dev), "Adam steps count from 1");
   QMC_REQUIRE(!sumsq_out_dev || sumsq_out_dev != sumsq_in_dev, "sumsq_out must not alias sumsq_in");
-  const bool layout_ok = obs->words_dev && R % 4 == 0 && R <= QMC_MAX_RANK && s_stride_r == 1 && s_stride_p == R &&
+  // the fused tail addresses S, m and v with the padded rank as the row stride: R must be its own padded
+  // rank (a power of two)
+  const bool layout_ok = obs->words_dev && R % 4 == 0 && (R & (R - 1)) == 0 && R <= QMC_MAX_RANK && s_stride_r == 1 && s_stride_p == R &&
                          s_stride_b == (int64_t)R * IJ && tile_warps > 0 && obs->n_sub == tile_warps &&
                          !(lik->flags & QMC_FORWARD_ONLY) &&
                          ((reinterpret_cast<uintptr_t>(S_dev) | reinterpret_cast<uintptr_t>(m_dev) |
                            reinterpret_cast<uintptr_t>(v_dev)) & 15) == 0;
   if (!layout_ok)
     return set_error(QMC_ERR_UNSUPPORTED, "fused S-step needs a lane-stream observation set with one tile per map, "
-                                          "pixel-major S/m/v (16-byte aligned) and a rank that is a multiple of 4");
+                                          "pixel-major S/m/v (16-byte aligned) and a rank of 4, 8, 16 or 32");
   if (sumsq_out_dev) QMC_CUDA_CHECK(cudaMemsetAsync(sumsq_out_dev, 0, sizeof(double) * B, (cudaStream_t)stream));
   FusedUpdate fu{S_dev, m_dev, v_dev, sumsq_in_dev, sumsq_out_dev, lr, beta1, beta2, eps, lam, project, step, step_dev};
   return gather_impl(S_dev, s_stride_b, s_stride_r, s_stride_p, C_dev, obs, lik, B, IJ, K, R, QMC_ALGO_LANES, tile_warps,

@@ -19,6 +19,10 @@ struct GatherParams {
   const int64_t* stream_off;  // lane-stream layout: first word of every (map, sub-tile) stream
   const int32_t* nrows;       // lane-stream layout: steps per stream (multiple of 4)
   int64_t stream_stride;      // lane-stream layout: > 0 = uniform stream capacity in words (no table look-up)
+  int n_runs;                 // lane-stream layout: run-table entries per lane (the stream starts with n_runs*32 words)
+  int word16;                 // lane-stream layout: 16-bit words (two groups per 16 bytes) instead of 32-bit ones
+  int lvl_bits;               // 16-bit words: bits of the level field
+  int has_cont;               // lane-stream layout: some band is split over several lanes (continuation rows in use)
   int lookahead;              // lanes kernel: CTAs resident on the device (prefetch distance in CTAs)
   int want_gs, want_gc;       // lanes kernel: which gradients the caller needs (QMC_SKIP_GS / QMC_SKIP_GC)
   // fused S-step (qmc_solver_s_step_fused): S is updated in place from the gS tile in shared memory
@@ -157,17 +161,38 @@ __device__ __forceinline__ int lds32i(uint32_t a) {
   return v;
 }
 
+// ---- lane-stream layout (qmc_obs_build_lanes, include/qmc_b200.h) ---------------------------------
+// 32-bit words: bit 31 = level & 1, bits 24..30 = level >> 1 (0xFF in bits 24..31 = padding), bits 0..14 = pixel.
+// 16-bit words: the top lvl_bits bits = level, the next bit = padding flag, the rest = pixel.
+// Run-table entry: bits 0..8 = gC row, bits 9..17 = band, bits 18..31 = groups.
 constexpr uint32_t LW_PIX_MASK = 0x7FFFu;
-constexpr uint32_t LW_BAND_MASK = 0x00FF8000u;
-constexpr int LW_BAND_SHIFT = 15;
+constexpr uint32_t LW_RUN_ROW_MASK = 0x1FFu;
+constexpr int LW_RUN_BAND_SHIFT = 9;
+constexpr int LW_RUN_LEN_SHIFT = 18;
+constexpr int LANES_CONT_ROWS = 32;  // gC rows K+1 .. K+32 of a warp: continuation pieces, one per lane
 
-constexpr int LANES_DEPTH = 4;  // groups of stream look-ahead per warp (power of two)
-static size_t lanes_smem_bytes(int K, int RP, int sub_pixels, int W, bool grad) {
-  const size_t TP = (size_t)sub_pixels * W;
-  size_t fl = TP * RP + (size_t)(K + 1) * RP;
-  if (grad) fl += TP * RP + (size_t)W * (K + 1) * RP;
-  fl += (size_t)W * LANES_DEPTH * 32 * 4;  // stream ring
-  return fl * sizeof(float) + 16;
+constexpr int LANES_LOOKAHEAD = 4;   // groups of stream look-ahead per warp
+__host__ __device__ inline int lanes_ring_slots(bool w16) { return w16 ? LANES_LOOKAHEAD / 2 : LANES_LOOKAHEAD; }
+
+// Shared memory of the lanes kernel (offsets in floats, every section 16-byte aligned):
+//   Ssm[TP][RP] | gSsm[TP][RP] | Csm[K+1][RP] | gCw[W][K+1+32][RP] | hdr[W][n_runs][32] | ring[W][slots][32][4]
+// Ssm comes first so that the address of an S row is the row offset plus a compile-time constant.
+struct LanesLayout {
+  uint32_t gS, C, gC, hdr, ring, total;
+};
+__host__ __device__ inline LanesLayout lanes_layout(int K, int RP, int TP, int W, bool grad, int n_runs, bool w16) {
+  LanesLayout L;
+  const uint32_t tile = ((uint32_t)TP * RP + 3u) & ~3u;
+  L.gS = tile;
+  L.C = L.gS + (grad ? tile : 0u);
+  L.gC = L.C + (((uint32_t)(K + 1) * RP + 3u) & ~3u);
+  L.hdr = L.gC + (grad ? (((uint32_t)W * (K + 1 + LANES_CONT_ROWS) * RP + 3u) & ~3u) : 0u);
+  L.ring = L.hdr + (uint32_t)W * n_runs * 32u;
+  L.total = L.ring + (uint32_t)W * lanes_ring_slots(w16) * 128u;
+  return L;
+}
+static size_t lanes_smem_bytes(int K, int RP, int sub_pixels, int W, bool grad, int n_runs, bool w16) {
+  return (size_t)lanes_layout(K, RP, sub_pixels * W, W, grad, n_runs, w16).total * sizeof(float) + 16;
 }
 // per-family launchers, one explicit instantiation per padded rank (qmc_gather_inst.cu)
 template <int RP> int launch_flat_rp(const GatherParams& prm, int epi, bool logd, bool grad, cudaStream_t st);

@@ -9,19 +9,33 @@ namespace qmc {
 // ------------------------------------------------------------------------------------------------
 // Same tiling and ownership as the tiled kernel (one CTA per (map, pixel tile), each warp owns a pixel
 // sub-tile exclusively), on the lane-stream layout of qmc_obs_build_lanes: every lane of a warp walks
-// the entries of ONE band at a time, so C[band] and the band's gC accumulator stay in registers (no
-// shared-memory traffic, no warp reduction, one plain store per (warp, band)); the builder guarantees
-// that the 32 entries of a step hit 32 different pixels, so the gS update is a plain shared-memory
-// read-modify-write, and that a lane changes band only at a group (4-step) boundary.  Per entry the
-// shared-memory pipe sees one S row read and one gS row read-modify-write; a padding lane re-reads a
-// row that a real lane of its quarter-warp reads anyway (a broadcast) and its update is predicated off.
+// a list of runs -- (band, number of 4-step groups) pairs from the stream's run table -- so C[band] and
+// the band's gC accumulator stay in registers (no shared-memory traffic, no warp reduction, one plain
+// store per run); the builder guarantees that the 32 entries of a step hit 32 different pixels, so the
+// gS update is a plain shared-memory read-modify-write, and that a lane changes band only at a group
+// (4-step) boundary.  Per entry the shared-memory pipe sees one S row read and one gS row
+// read-modify-write; a padding lane re-reads a row that a real lane of its quarter-warp reads anyway
+// (a broadcast) and its update is predicated off.
+//
+// Stream words carry only (level, padding flag, tile-local pixel): 16 bits when that fits (W16: one
+// 16-byte load per lane brings two groups), 32 bits otherwise.  The band comes from the run table.
+//
+// A band may be split over several lanes (runs cut at group boundaries so that all lanes get the same
+// number of groups).  The piece that starts a band stores its gC partial to the band's row of the warp's
+// private gC copy; a continuation piece is always the first run of its lane and stores to a row of its
+// own (K+1+lane), merged into the band's row when the warp is done -- no atomics on the way.
 //
 // The warps of a CTA are autonomous: each stages its own S slice (its own TMA bulk copy and
 // mbarrier), zeroes and later writes its own gS slice, and keeps a private gC copy; the only CTA-wide
 // synchronisation is one early barrier after C is staged.  The last warp to finish folds the gC
 // copies and the NLL partials and writes them out.
-// Shared memory (floats): ring[W][4][32][4] | Ssm[TP][RP] | gSsm[TP][RP] | Csm[K+1][RP] | gCw[W][K+1][RP]; band row K is a
-// dummy that absorbs the flush of a lane that owns no band.
+// Shared memory: see lanes_layout (qmc_gather_common.cuh); band row K of Csm / gCw is a dummy (zeros /
+// absorbs the flush of a lane that owns nothing).
+//
+// Convergence: the gS read-modify-writes of a step may touch a pixel that another lane touched in an
+// earlier step, so the warp must execute them in step order.  The only divergent code of the main loop is
+// the run switch; it is followed by __syncwarp(), and everything after it up to the next switch is
+// straight-line predicated code, which keeps the warp converged.
 
 // ---- packed fp32x2 arithmetic (FFMA2/FMUL2/FADD2, sm_100) --------------------------------------
 struct f2 {
@@ -59,14 +73,12 @@ __device__ __forceinline__ void sts32_if(uint32_t a, float v, bool p) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" ::"r"(a), "f"(v), "r"((int)p) : "memory");
 }
 
-__device__ __forceinline__ uint4 ldg_u4(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-// 16-byte asynchronous global -> shared copy (LDGSTS, L2 only) and its in-order group accounting
+// 16-byte / 4-byte asynchronous global -> shared copies (LDGSTS) and their in-order group accounting
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -76,12 +88,12 @@ __device__ __forceinline__ uint4 lds128_u4(uint32_t a) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t lds32u(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// lane-stream word (qmc_obs_build_lanes): bit 31 = level & 1, bits 24..30 = level >> 1, bits 15..23 = band,
-// bits 0..14 = tile-local pixel; level 0xFF (bits 24..31 all set) = padding
-__device__ __forceinline__ bool lw_valid(uint32_t w) { return w < 0xFF000000u; }
-__device__ __forceinline__ int lw_level(uint32_t w) { return (int)(((w >> 23) & 0xFEu) | (w >> 31)); }
 
 // GMODE: 0 = NLL only, 1 = both gradients, 2 = gC only (QMC_SKIP_GS), 3 = gS only (QMC_SKIP_GC),
 //        4 = gS only, consumed in place by the fused Adam update of S (qmc_solver_s_step_fused)
@@ -90,17 +102,19 @@ __device__ __forceinline__ int lw_level(uint32_t w) { return (int)(((w >> 23) & 
 constexpr uint32_t LANES_ZERO_BYTES = 64 * 1024;
 __device__ __align__(128) unsigned char g_lanes_zero[LANES_ZERO_BYTES];
 
-template <int RP, int EPI, bool LOGD, int GMODE>
+template <int RP, int EPI, bool LOGD, int GMODE, bool W16>
 __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams prm) {
   constexpr bool GRAD = GMODE != 0;
+  constexpr int SLOTS = W16 ? LANES_LOOKAHEAD / 2 : LANES_LOOKAHEAD;  // ring slots of 16 bytes per lane
   extern __shared__ __align__(16) float smem[];
   const int W = prm.tile_warps, K = prm.K;
   const int TP = prm.sub_pixels * W;
-  float* ring = smem;  // [W][LANES_DEPTH][32 lanes][4 words], first: 16-byte aligned for any rank
-  float* Ssm = ring + (size_t)W * LANES_DEPTH * 32 * 4;
-  float* gSsm = Ssm + (size_t)TP * RP;
-  float* Csm = gSsm + (GRAD ? (size_t)TP * RP : 0);
-  float* gCw = Csm + (size_t)(K + 1) * RP;
+  const LanesLayout L = lanes_layout(K, RP, TP, W, GRAD, prm.n_runs, W16);
+  float* Ssm = smem;
+  float* gSsm = smem + L.gS;
+  float* Csm = smem + L.C;
+  float* gCw = smem + L.gC;
+  constexpr int XROWS = 1 + LANES_CONT_ROWS;  // dummy row + continuation rows behind the K band rows
   __shared__ uint64_t mbar[8];
   __shared__ double wsum[8];
   __shared__ int done;
@@ -116,6 +130,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   constexpr bool do_gs = GMODE == 1 || GMODE == 3 || GMODE == 4, do_gc = GMODE == 1 || GMODE == 2;
   constexpr bool FUSE = GMODE == 4;  // bulk layout guaranteed by the host
   float* gSb = (do_gs && !FUSE) ? prm.gS + b * prm.sB : nullptr;
+  // pixel-major storage ([IJ][R], R == RP a multiple of 4): a slice is one contiguous, 16-byte aligned run
   const bool bulk = (prm.sR == 1 && prm.sP == RP && prm.R == RP && (RP % 4) == 0 &&
                      ((reinterpret_cast<uintptr_t>(Sb) | ((do_gs && !FUSE) ? reinterpret_cast<uintptr_t>(gSb) : 0)) & 15) == 0);
   // this warp's pixel slice of the tile
@@ -126,28 +141,31 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
 
   // ---- prologue: every warp stages its own slice; one CTA barrier for C -------------------------
   const uint32_t slice_bytes = (uint32_t)sln * RP * sizeof(float);
-  const bool zero_by_copy = bulk && do_gs && slice_bytes <= LANES_ZERO_BYTES;
-  if (bulk && sln > 0 && lane == 0) {
+  const bool zero_by_copy = do_gs && (RP % 4) == 0 && slice_bytes <= LANES_ZERO_BYTES;  // the shared-memory side is always aligned
+  const bool use_bar = sln > 0 && (bulk || zero_by_copy);
+  if (use_bar && lane == 0) {
     mbar_init(&mbar[warp], 1);
-    mbar_expect_tx(&mbar[warp], zero_by_copy ? 2 * slice_bytes : slice_bytes);
-    bulk_g2s(Sw, Sb + (int64_t)(p0 + sl0) * RP, slice_bytes, &mbar[warp]);
+    mbar_expect_tx(&mbar[warp], (bulk ? slice_bytes : 0u) + (zero_by_copy ? slice_bytes : 0u));
+    if (bulk) bulk_g2s(Sw, Sb + (int64_t)(p0 + sl0) * RP, slice_bytes, &mbar[warp]);
     if (zero_by_copy) bulk_g2s(gSw, g_lanes_zero, slice_bytes, &mbar[warp]);
   }
   if (threadIdx.x == 0) done = 0;
   // every global load of the prologue is issued before anything waits on one of them (the warp issues in
   // order: a store of loaded data would hold back the loads behind it for a full memory round trip)
   const int64_t stream = (int64_t)b * prm.n_sub + (int64_t)tile * W + warp;
-  const uint4* gp = reinterpret_cast<const uint4*>(
-                        prm.words + (prm.stream_stride > 0 ? stream * prm.stream_stride : prm.stream_off[stream])) + lane;
-  // LANES_DEPTH groups of look-ahead through a per-lane ring in shared memory, filled by asynchronous
-  // copies (the stream is read once, straight from DRAM; cp.async groups complete in order, which plain
-  // loads sharing a scoreboard do not guarantee).  Every stream has room for at least LANES_DEPTH groups, so
+  const uint32_t* sbase = prm.words + (prm.stream_stride > 0 ? stream * prm.stream_stride : prm.stream_off[stream]);
+  const uint4* gp = reinterpret_cast<const uint4*>(sbase + (size_t)prm.n_runs * 32) + lane;
+  // the run table of the stream (n_runs entries per lane) and SLOTS ring slots of look-ahead, filled by
+  // asynchronous copies (the stream is read once, straight from DRAM; cp.async groups complete in order, which
+  // plain loads sharing a scoreboard do not guarantee).  Every stream has room for at least SLOTS slots, so
   // the first copies need not know its length.
-  const uint32_t ring_a = smem_u32(ring) + (uint32_t)((warp * LANES_DEPTH) * 32 + lane) * 16u;
+  const uint32_t hdr_a = smem_u32(smem + L.hdr) + (uint32_t)(warp * prm.n_runs * 32 + lane) * 4u;
+  const uint32_t ring_a = smem_u32(smem + L.ring) + (uint32_t)((warp * SLOTS) * 32 + lane) * 16u;
+  for (int i = 0; i < prm.n_runs; ++i) cp_async4(hdr_a + i * 128, sbase + i * 32 + lane);
 #pragma unroll
-  for (int d = 0; d < LANES_DEPTH; ++d) {
+  for (int d = 0; d < SLOTS; ++d) {
     cp_async16(ring_a + d * 512, gp + d * 32);
-    cp_async_commit();
+    cp_async_commit();  // the first group also holds the run table
   }
   const int nrows_v = __ldg(prm.nrows + stream);
   const int cn = RP * (K + 1);
@@ -170,11 +188,16 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       const char* c2 = reinterpret_cast<const char*>(prm.C + (int64_t)b2 * prm.R * K);
       for (int o = (lane - 24) * 128; o < prm.R * K * 4; o += 8 * 128) prefetch_l2(c2 + o);
     }
+    const int np2 = min(TP, prm.IJ - tile2 * TP);
+    const int s20 = min(warp * prm.sub_pixels, np2), s2n = min((warp + 1) * prm.sub_pixels, np2) - s20;
     if (bulk) {
-      const int np2 = min(TP, prm.IJ - tile2 * TP);
-      const int s20 = min(warp * prm.sub_pixels, np2), s2n = min((warp + 1) * prm.sub_pixels, np2) - s20;
       const char* s2 = reinterpret_cast<const char*>(prm.S + b2 * prm.sB + (int64_t)(tile2 * TP + s20) * RP);
       for (int o = lane * 128; o < s2n * RP * 4; o += 32 * 128) prefetch_l2(s2 + o);
+    } else if (prm.sP == 1) {  // emitter-major: R contiguous runs of the slice's pixels
+      for (int r = 0; r < prm.R; ++r) {
+        const char* s2 = reinterpret_cast<const char*>(prm.S + b2 * prm.sB + r * prm.sR + (tile2 * TP + s20));
+        for (int o = lane * 128; o < s2n * 4 + 128; o += 32 * 128) prefetch_l2(s2 + o);
+      }
     }
   }
   if (FUSE && sln > 0) {  // the Adam moments of this warp's slice are needed at the very end: pull them into L2 now
@@ -186,8 +209,9 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     }
   }
   if (!bulk) {
-    // emitter-major storage (the reference's): coalesced row reads transposed into [p][r]; the loads of
-    // SU pixels per lane are all in flight before the first store waits for one
+    // emitter-major storage (the reference's): every lane gathers the R values of one pixel with coalesced
+    // row reads and writes them as one row [p][0..RP) -- the transposition happens in registers; the loads
+    // of SU pixels per lane are all in flight before the first store waits for one
     constexpr int SU = RP <= 8 ? 4 : 1;
     for (int i0 = 0; i0 < sln; i0 += 32 * SU) {
       float tmp[SU][RP];
@@ -202,22 +226,28 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       for (int u = 0; u < SU; ++u) {
         const int pl = i0 + u * 32 + lane;
         if (pl < sln) {
+          if (RP % 4 == 0) {
 #pragma unroll
-          for (int r = 0; r < RP; ++r) Sw[pl * RP + r] = tmp[u][r];
+            for (int r = 0; r < RP; r += 4)
+              *reinterpret_cast<float4*>(Sw + pl * RP + r) = make_float4(tmp[u][r], tmp[u][r + 1], tmp[u][r + 2], tmp[u][r + 3]);
+          } else {
+#pragma unroll
+            for (int r = 0; r < RP; ++r) Sw[pl * RP + r] = tmp[u][r];
+          }
         }
       }
     }
   }
   if (GRAD) {
+    float* zc = gCw + (size_t)warp * (K + XROWS) * RP;
     if (RP % 4 == 0) {
       float4* z = reinterpret_cast<float4*>(gSw);
       for (int i = lane; i < ((do_gs && !zero_by_copy) ? sln * (RP / 4) : 0); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4* zc = reinterpret_cast<float4*>(gCw + (size_t)warp * (K + 1) * RP);
-      for (int i = lane; i < (K + 1) * (RP / 4); i += 32) zc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4* zc4 = reinterpret_cast<float4*>(zc);
+      for (int i = lane; i < (K + XROWS) * (RP / 4); i += 32) zc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       for (int i = lane; i < (do_gs ? sln * RP : 0); i += 32) gSw[i] = 0.0f;
-      float* zc = gCw + (size_t)warp * (K + 1) * RP;
-      for (int i = lane; i < (K + 1) * RP; i += 32) zc[i] = 0.0f;
+      for (int i = lane; i < (K + XROWS) * RP; i += 32) zc[i] = 0.0f;
     }
   }
   {
@@ -230,27 +260,27 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     }
   }
   const int ngroups = nrows_v >> 2;
-  const int last = max(ngroups - 1, 0);
   __syncthreads();  // Csm and `done` are ready; the slices are private to their warps
-  if (bulk && sln > 0) mbar_wait(&mbar[warp], 0);
+  if (use_bar) mbar_wait(&mbar[warp], 0);
   __syncwarp();
 
   constexpr uint32_t ROWB = RP * sizeof(float);
   const uint32_t S_a = smem_u32(Ssm), C_a = smem_u32(Csm);
   const uint32_t gS_delta = smem_u32(gSsm) - S_a;
-  const uint32_t gC_a = smem_u32(gCw + (size_t)warp * (K + 1) * RP);
+  const uint32_t gC_a = smem_u32(gCw + (size_t)warp * (K + XROWS) * RP);
 
   float nll_part = 0.0f;               // generic epilogues: sum of -log P
   f2 nl2 = mk2(0.0f, 0.0f);            // packed one-bit epilogue: sum of log2 P, two partial sums
   float c[RP], acc[RP];
-  uint32_t cur_key = (uint32_t)K << LW_BAND_SHIFT;  // dummy band until the first group
+  uint32_t cur_row = (uint32_t)K;      // gC row of the current run (dummy until the first run)
+  int run_left = 0;                    // groups left in the current run
+  uint32_t run_a = hdr_a;              // next run-table entry of this lane
 #pragma unroll
   for (int r = 0; r < RP; ++r) { c[r] = 0.0f; acc[r] = 0.0f; }
 
-  auto switch_band = [&](uint32_t key) {
-    // one plain store per (warp, band): the band is this lane's alone in this stream
+  auto flush_run = [&]() {  // one plain store per run: the row is this lane's alone
     if (GRAD) {
-      const uint32_t grow = gC_a + (cur_key >> LW_BAND_SHIFT) * ROWB;
+      const uint32_t grow = gC_a + cur_row * ROWB;
       if (RP % 4 == 0) {
 #pragma unroll
         for (int r = 0; r < RP; r += 4) sts128(grow + r * 4, make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]));
@@ -259,8 +289,14 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
         for (int r = 0; r < RP; ++r) sts32(grow + r * 4, acc[r]);
       }
     }
-    cur_key = key;
-    const uint32_t crow = C_a + (key >> LW_BAND_SHIFT) * ROWB;
+  };
+  auto next_run = [&]() {
+    flush_run();
+    const uint32_t e = lds32u(run_a);
+    run_a += 128;
+    cur_row = e & LW_RUN_ROW_MASK;
+    run_left = (int)(e >> LW_RUN_LEN_SHIFT);
+    const uint32_t crow = C_a + ((e >> LW_RUN_BAND_SHIFT) & 0x1FFu) * ROWB;
     if (RP % 4 == 0) {
 #pragma unroll
       for (int r = 0; r < RP; r += 4) {
@@ -282,19 +318,29 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   const f2 nthr2 = bc2(-prm.thr), inva2 = bc2(prm.inv_a * kS);
   const f2 kg2 = bc2(kInvSqrtPi * prm.inv_a);
 
+  // word decoding.  cw: the word with its level field at the top (bit 31 = the one-bit level)
+  constexpr int SH = RP == 1 ? 2 : RP == 2 ? 3 : RP == 4 ? 4 : RP == 8 ? 5 : RP == 16 ? 6 : 7;  // log2(ROWB)
+  const int lvl_bits = (W16 && EPI != EPI_ONEBIT) ? prm.lvl_bits : 1;
+  const uint32_t pixm16 = (1u << (15 - lvl_bits)) - 1u;
+  auto w_ok = [&](uint32_t cw) -> bool { return W16 ? ((cw >> (31 - lvl_bits)) & 1u) == 0u : cw < 0xFF000000u; };
+  auto w_off = [&](uint32_t cw) -> uint32_t {  // byte offset of the pixel's row in the S / gS tiles
+    return W16 ? ((cw >> (16 - SH)) & (pixm16 << SH)) : ((cw & LW_PIX_MASK) << SH);
+  };
+  auto w_level = [&](uint32_t cw) -> int { return W16 ? (int)(cw >> (32 - lvl_bits)) : (int)(((cw >> 23) & 0xFEu) | (cw >> 31)); };
+
   // The gS updates of a group are applied one group late, in the same straight-line block as the next
   // group's likelihood: the read-modify-write chain (LDS -> FFMA2 -> STS, four in a row, ordered) then
   // overlaps the arithmetic instead of stalling the warp on the short scoreboard.
-  uint32_t pw[4];   // words of the pending group (0xFF000000 = padding, pixel 0: nothing to store)
-  float pg[4];      // their g = dNLL/dx
+  uint32_t pw[4];   // pending group: row offsets
+  float pg[4];      // their g = dNLL/dx; 0 for padding, and a zero g has nothing to store
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { pw[j] = 0xFF000000u; pg[j] = 0.0f; }
+  for (int j = 0; j < 4; ++j) { pw[j] = 0u; pg[j] = 0.0f; }
   auto apply_pending = [&](const float (&cp)[RP]) {  // cp: the C row of the pending group
     if (!do_gs) return;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t rs = S_a + gS_delta + (pw[j] & LW_PIX_MASK) * ROWB;
-      const bool pok = lw_valid(pw[j]);
+      const uint32_t rs = S_a + gS_delta + pw[j];
+      const bool pok = pg[j] != 0.0f;  // padding lanes (g = 0) must not store: their row is a real lane's
       if (RP % 4 == 0) {
         const f2 g2 = bc2(pg[j]);
 #pragma unroll
@@ -313,36 +359,36 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     }
   };
 
-  auto group = [&](const uint4 wv) {
-    const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
-    __syncwarp();  // steps are applied in program order by the converged warp (a later step may touch the same pixel from another lane)
+  auto group = [&](const uint32_t (&w)[4]) {
     float g[4], sv[4][RP];
-    uint32_t srow[4];
+    uint32_t soff[4];
     bool ok[4];
     float t[4];
     // program order matters to ptxas (shared-memory loads are not moved above stores that may alias): this
-    // group's S rows and, on a band change, its C row are loaded first, then the pending gS updates are
+    // group's S rows and, on a run change, its C row are loaded first, then the pending gS updates are
     // issued, and the arithmetic below fills their latency
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      ok[j] = lw_valid(w[j]);
-      srow[j] = S_a + (w[j] & LW_PIX_MASK) * ROWB;
+      ok[j] = w_ok(w[j]);
+      soff[j] = w_off(w[j]);
+      const uint32_t srow = S_a + soff[j];
       if (RP % 4 == 0) {
 #pragma unroll
         for (int r = 0; r < RP; r += 4) {
-          const float4 s4 = lds128_ro(srow[j] + r * 4);  // padding words point at a real lane's row (broadcast)
+          const float4 s4 = lds128_ro(srow + r * 4);  // padding words point at a real lane's row (broadcast)
           sv[j][r] = s4.x; sv[j][r + 1] = s4.y; sv[j][r + 2] = s4.z; sv[j][r + 3] = s4.w;
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < RP; ++r) sv[j][r] = lds32_ro(srow[j] + r * 4);
+        for (int r = 0; r < RP; ++r) sv[j][r] = lds32_ro(srow + r * 4);
       }
     }
     float cp[RP];
 #pragma unroll
     for (int r = 0; r < RP; ++r) cp[r] = c[r];
-    const uint32_t key = w[0] & LW_BAND_MASK;
-    if (key != cur_key) switch_band(key);  // lanes change band only at group boundaries
+    if (run_left == 0) next_run();  // lanes change band only at group boundaries
+    __syncwarp();  // reconverged: the gS updates below are applied in step order by the whole warp
+    --run_left;
     apply_pending(cp);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -360,8 +406,8 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       }
     }
     if (EPI == EPI_ONEBIT && !LOGD) {
-      // P = 0.5 erfc(u), u = (x - thr) * (level ? -1 : +1) / a.  Padding: x := huge, level bit set ->
-      // u = -inf -> E = 0, P = 1, log P = 0, g = 0 with no further selects.
+      // P = 0.5 erfc(u), u = (x - thr) * (level ? -1 : +1) / a.  Padding: x := huge, level bit set (padding words
+      // have all level bits set) -> u = -inf -> E = 0, P = 1, log P = 0, g = 0 with no further selects.
 #pragma unroll
       for (int j = 0; j < 4; j += 2) {
         const f2 x2 = mk2(ok[j] ? t[j] : 3.0e38f, ok[j + 1] ? t[j + 1] : 3.0e38f);
@@ -399,7 +445,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int lv = lw_level(w[j]);
+        const int lv = ok[j] ? w_level(w[j]) : 0;
         float dxdt;
         const BinEval ev = eval_entry<EPI, LOGD>(prm, t[j], (EPI == EPI_ONEBIT) ? (lv & 1) : lv, dxdt);
         nll_part -= ok[j] ? ev.logp : 0.0f;
@@ -424,25 +470,61 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       for (int j = 0; j < 4; ++j) gc_step(j);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { pw[j] = w[j]; pg[j] = g[j]; }
+    for (int j = 0; j < 4; ++j) { pw[j] = soff[j]; pg[j] = g[j]; }
   };
 
-  int slot = 0;
+  {
+    const int nslots = W16 ? (ngroups + 1) >> 1 : ngroups;
+    const int last = max(nslots - 1, 0);
+    int slot = 0, gleft = ngroups;
 #pragma unroll 1
-  for (int grp = 0; grp < ngroups; ++grp) {
-    cp_async_wait<LANES_DEPTH - 1>();  // group grp has landed (this lane reads only what it copied itself)
-    const uint32_t sa = ring_a + slot * 512;
-    const uint4 wv = lds128_u4(sa);
-    cp_async16(sa, gp + (size_t)min(grp + LANES_DEPTH, last) * 32);  // refill the slot just read
-    cp_async_commit();
-    slot = (slot + 1) & (LANES_DEPTH - 1);
-    group(wv);
+    for (int s = 0; s < nslots; ++s) {
+      cp_async_wait<SLOTS - 1>();  // slot s has landed (this lane reads only what it copied itself)
+      const uint32_t sa = ring_a + slot * 512;
+      const uint4 wv = lds128_u4(sa);
+      cp_async16(sa, gp + (size_t)min(s + SLOTS, last) * 32);  // refill the slot just read
+      cp_async_commit();
+      slot = (slot + 1) & (SLOTS - 1);
+      if (W16) {
+        // two groups per slot; 16-bit words moved to the top half of a 32-bit one
+        const int ge = min(2, gleft);
+        gleft -= 2;
+#pragma unroll 1
+        for (int q = 0; q < ge; ++q) {
+          const uint32_t a = q ? wv.z : wv.x, bq = q ? wv.w : wv.y;
+          const uint32_t w4[4] = {a << 16, a, bq << 16, bq};
+          group(w4);
+        }
+      } else {
+        const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
+        group(w4);
+      }
+    }
   }
   cp_async_wait<0>();
   __syncwarp();
   apply_pending(c);
   __syncwarp();
-  switch_band((uint32_t)K << LW_BAND_SHIFT);  // flush the last band
+  flush_run();  // the last run
+  if (do_gc && prm.has_cont) {
+    // merge this warp's continuation rows into their bands' rows (a band may be continued by several lanes:
+    // lanes whose bands coincide take turns)
+    __syncwarp();
+    const uint32_t e0 = lds32u(hdr_a);
+    const uint32_t row0 = e0 & LW_RUN_ROW_MASK, band0 = (e0 >> LW_RUN_BAND_SHIFT) & 0x1FFu;
+    bool todo = row0 > (uint32_t)K;
+    while (__any_sync(0xffffffffu, todo)) {
+      const unsigned m = __match_any_sync(0xffffffffu, todo ? band0 : (0x10000u + lane));
+      const bool turn = todo && (__ffs(m) - 1) == lane;
+      if (turn) {
+        const uint32_t dst = gC_a + band0 * ROWB, src = gC_a + row0 * ROWB;
+#pragma unroll
+        for (int r = 0; r < RP; ++r) sts32(dst + r * 4, lds32(dst + r * 4) + lds32(src + r * 4));
+      }
+      todo = todo && !turn;
+      __syncwarp();
+    }
+  }
 
   // ---- epilogue: own gS slice out, then the last warp folds gC and the NLL -----------------------
   if (EPI == EPI_ONEBIT && !LOGD) {
@@ -454,7 +536,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   if (lane == 0) wsum[warp] = wsumv;
   if (FUSE && sln > 0) {
     // Adam + regulariser + projection on this warp's slice, straight from the S and gS tiles in shared
-    // memory: p, m, v are contiguous in the pixel-major storage
+    // memory: p, m, v are contiguous in the pixel-major storage (row stride RP == R, checked by the host)
     __syncwarp();
     const int tstep = prm.step + (prm.step_dev ? *prm.step_dev : 0);
     const float bc1 = 1.0f - powf(prm.beta1, (float)tstep), bc2 = 1.0f - powf(prm.beta2, (float)tstep);
@@ -503,11 +585,24 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       __syncwarp();
       if (lane == 0) bulk_s2g(gSb + (int64_t)(p0 + sl0) * RP, gSw, (uint32_t)sln * RP * sizeof(float));
     } else {
+      // emitter-major: one 16-byte row read per lane and pixel, R coalesced row writes
       __syncwarp();
+      for (int pl = lane; pl < sln; pl += 32) {
+        float row[RP];
+        if (RP % 4 == 0) {
 #pragma unroll
-      for (int r = 0; r < RP; ++r)
-        if (r < prm.R)
-          for (int pl = lane; pl < sln; pl += 32) gSb[r * prm.sR + (int64_t)(p0 + sl0 + pl) * prm.sP] = gSw[pl * RP + r];
+          for (int r = 0; r < RP; r += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(gSw + pl * RP + r);
+            row[r] = v.x; row[r + 1] = v.y; row[r + 2] = v.z; row[r + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < RP; ++r) row[r] = gSw[pl * RP + r];
+        }
+#pragma unroll
+        for (int r = 0; r < RP; ++r)
+          if (r < prm.R) gSb[r * prm.sR + (int64_t)(p0 + sl0 + pl) * prm.sP] = row[r];
+      }
     }
   }
   __threadfence_block();
@@ -530,7 +625,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
         if (r >= prm.R) break;
         for (int k = lane; k < K; k += 32) {
           float v = 0.0f;
-          for (int w2 = 0; w2 < W; ++w2) v += gCw[((size_t)w2 * (K + 1) + k) * RP + r];
+          for (int w2 = 0; w2 < W; ++w2) v += gCw[((size_t)w2 * (K + XROWS) + k) * RP + r];
           if (prm.tiles_per_map == 1) gCb[r * K + k] = v;
           else atomicAdd(gCb + r * K + k, v);
         }
@@ -540,15 +635,15 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   if (do_gs && !FUSE && bulk && sln > 0 && lane == 0) bulk_wait_all();  // the slice must stay alive until the engine has read it
 }
 
-template <int RP, int EPI, bool LOGD, bool GRAD>
+template <int RP, int EPI, bool LOGD, bool GRAD, bool W16>
 static int launch_lanes_one(const GatherParams& prm, cudaStream_t st) {
-  const size_t smem = lanes_smem_bytes(prm.K, RP, prm.sub_pixels, prm.tile_warps, GRAD);
-  auto kern = gather_lanes_kernel<RP, EPI, LOGD, 0>;
+  const size_t smem = lanes_smem_bytes(prm.K, RP, prm.sub_pixels, prm.tile_warps, GRAD, prm.n_runs, W16);
+  auto kern = gather_lanes_kernel<RP, EPI, LOGD, 0, W16>;
   if (GRAD) {
-    if (prm.fuse_update && RP % 4 == 0) kern = gather_lanes_kernel<RP, EPI, LOGD, (GRAD && RP % 4 == 0) ? 4 : 0>;
-    else if (prm.want_gs && prm.want_gc) kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 1 : 0>;
-    else if (prm.want_gc) kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 2 : 0>;
-    else kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 3 : 0>;
+    if (prm.fuse_update && RP % 4 == 0) kern = gather_lanes_kernel<RP, EPI, LOGD, (GRAD && RP % 4 == 0) ? 4 : 0, W16>;
+    else if (prm.want_gs && prm.want_gc) kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 1 : 0, W16>;
+    else if (prm.want_gc) kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 2 : 0, W16>;
+    else kern = gather_lanes_kernel<RP, EPI, LOGD, GRAD ? 3 : 0, W16>;
   }
   QMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ctas = (int64_t)prm.B * prm.tiles_per_map;
@@ -561,7 +656,11 @@ static int launch_lanes_one(const GatherParams& prm, cudaStream_t st) {
 
 template <int RP>
 int launch_lanes_rp(const GatherParams& prm, int epi, bool logd, bool grad, cudaStream_t st) {
-#define QMC_GO(E, L, G) return launch_lanes_one<RP, E, L, G>(prm, st)
+#define QMC_GO(E, L, G)                                                   \
+  do {                                                                    \
+    if (prm.word16) return launch_lanes_one<RP, E, L, G, true>(prm, st);  \
+    return launch_lanes_one<RP, E, L, G, false>(prm, st);                 \
+  } while (0)
   QMC_GATHER_SWITCH(QMC_GO);
 #undef QMC_GO
   return QMC_OK;

@@ -192,7 +192,7 @@ __global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict_
                                  const int64_t* __restrict__ row_off, int64_t n_streams, int K, int IJ, int n_sub,
                                  int sub_pixels, int tile_warps, const int64_t* __restrict__ stream_off,
                                  uint32_t* __restrict__ words, int32_t* __restrict__ nrows,
-                                 int32_t* __restrict__ overflow) {
+                                 int32_t* __restrict__ overflow, int n_runs, int word16, int lvl_bits) {
   extern __shared__ __align__(16) unsigned char lanes_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -210,6 +210,7 @@ __global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict_
   const int st = (int)(s % n_sub);
   const int TP = tile_warps * sub_pixels;
   const int p0 = (st / tile_warps) * TP;  // first pixel of the tile this sub-tile belongs to
+  const uint32_t own0 = (uint32_t)((st % tile_warps) * sub_pixels);  // tile-local: first pixel of this sub-tile (idle padding points here)
   // rank the bands by size (descending, ties by band index)
   for (int k = lane; k < K; k += 32) {
     const int64_t ck = row_off[row0 + k + 1] - row_off[row0 + k];
@@ -295,8 +296,25 @@ __global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict_
   int g = -1, band = K, cur = 0, end = 0;  // band K: the dummy band of a lane that owns nothing
   unsigned long long cnt = 0;              // candidates left per bank group, for band cnt_band
   int cnt_band = -1;
-  const int64_t out0 = stream_off[s];
-  const int cap = (int)((stream_off[s + 1] - out0) >> 5);
+  // stream: run table (n_runs entries per lane, [entry][lane]) followed by the words in 512-byte slots
+  // (32 lanes x 16 bytes: four 32-bit words = one group, or eight 16-bit words = two groups)
+  uint32_t* const table = words + stream_off[s];
+  const int64_t out0 = stream_off[s] + (int64_t)n_runs * 32;
+  const int cap = (int)((stream_off[s + 1] - out0) >> 7) * (word16 ? 8 : 4);  // steps
+  uint16_t* const words16 = reinterpret_cast<uint16_t*>(words + out0);
+  auto put_word = [&](int t, uint32_t lv, bool pad, uint32_t pix) {
+    const int gi = t >> 2;
+    if (word16) {
+      const uint32_t lvf = pad ? ((1u << lvl_bits) - 1u) : lv;  // padding: all level bits set (the one-bit epilogue relies on it)
+      words16[((int64_t)(gi >> 1) * 32 + lane) * 8 + (gi & 1) * 4 + (t & 3)] =
+          (uint16_t)((lvf << (16 - lvl_bits)) | ((pad ? 1u : 0u) << (15 - lvl_bits)) | pix);
+    } else {
+      const uint32_t lvf = pad ? LANE_PAD_LEVEL : lv;
+      words[out0 + ((int64_t)gi * 32 + lane) * LANE_GROUP + (t & 3)] = ((lvf & 1u) << 31) | ((lvf >> 1) << 24) | pix;
+    }
+  };
+  int nrun = 0, run_band = -1, run_beg = 0;  // run table of this lane
+  for (int i = 0; i < n_runs; ++i) table[i * 32 + lane] = 0u;
   int step = 0;
   while (__any_sync(0xffffffffu, left > 0)) {
     // move on to the lane's next non-empty band -- only at a group boundary, so that the gather
@@ -312,6 +330,13 @@ __global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict_
           const int c0 = (int)(row_off[row0 + nb] - beg), e0 = (int)(row_off[row0 + nb + 1] - beg);
           if (e0 > c0) { band = nb; cur = c0; end = e0; }
         }
+      }
+      if (band != run_band) {  // a new run: close the previous entry, open the next
+        if (nrun > 0 && nrun <= n_runs)
+          table[(nrun - 1) * 32 + lane] = (uint32_t)run_band | ((uint32_t)run_band << 9) | ((uint32_t)((step >> 2) - run_beg) << 18);
+        run_band = band;
+        run_beg = step >> 2;
+        ++nrun;
       }
     }
     const bool has = cur < end;
@@ -376,7 +401,7 @@ __global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict_
     const unsigned wonq = wonmask & (0xffu << (lane & 24));
     const int srcl = wonq ? __ffs(wonq) - 1 : (wonmask ? __ffs(wonmask) - 1 : lane);
     const int padpix = __shfl_sync(0xffffffffu, pix, srcl);
-    uint32_t word = (LANE_PAD_LEVEL << 24) | ((uint32_t)band << 15) | (uint32_t)(wonmask ? padpix : 0);
+    int lvw = 0;
     if (won) {
       const int lv = lvl[beg + q];
       if (q != cur) {  // move the chosen entry to the front of what is left of the row
@@ -389,21 +414,25 @@ __global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict_
       --left;
       if (((cnt >> (8 * (pix & 7))) & 0xFFull) == 255) cnt_band = -1;  // saturated: recount
       else cnt -= 1ull << (8 * (pix & 7));
-      word = ((uint32_t)(lv & 1) << 31) | ((uint32_t)(lv >> 1) << 24) | ((uint32_t)band << 15) | (uint32_t)pix;
+      lvw = lv;
     }
-    if (step < cap) words[out0 + ((int64_t)(step >> 2) * 32 + lane) * LANE_GROUP + (step & 3)] = word;
+    if (step < cap) put_word(step, (uint32_t)lvw, !won, won ? (uint32_t)pix : (wonmask ? (uint32_t)padpix : own0));
     ++step;
     if (step > cap + 4096) break;  // hopeless: report and stop
   }
-  // pad the last group
-  const uint32_t padw = (LANE_PAD_LEVEL << 24) | ((uint32_t)band << 15);
+  // pad the last group; idle padding points at the first pixel of the stream's own sub-tile (rows the warp itself staged)
   while (step & (LANE_GROUP - 1)) {
-    if (step < cap) words[out0 + ((int64_t)(step >> 2) * 32 + lane) * LANE_GROUP + (step & 3)] = padw;
+    if (step < cap) put_word(step, 0u, true, own0);
     ++step;
   }
+  // the last run never ends (a lane that has run out keeps walking padding words of its last band); a lane
+  // that never opened a run walks the dummy band K
+  if (nrun == 0) { run_band = K; nrun = 1; }
+  if (nrun <= n_runs) table[(nrun - 1) * 32 + lane] = (uint32_t)run_band | ((uint32_t)run_band << 9) | (0x3FFFu << 18);
+  const bool bad_runs = __any_sync(0xffffffffu, nrun > n_runs);
   if (lane == 0) {
     nrows[s] = step <= cap ? step : cap;
-    if (step > cap) atomicExch(overflow, 1);
+    if (step > cap || bad_runs) atomicExch(overflow, 1);
   }
 }
 
@@ -518,13 +547,18 @@ extern "C" int qmc_quantize_levels(const float* noisy_dev, int64_t n, const floa
 extern "C" int qmc_obs_build_lanes(int32_t* idx_rows_dev, uint8_t* lvl_rows_dev, const int64_t* row_off_dev,
                                    int B, int K, int IJ, int n_sub, int sub_pixels, int tile_warps,
                                    const int64_t* stream_off_dev, uint32_t* words_out_dev,
-                                   int32_t* nrows_out_dev, int32_t* overflow_dev, void* stream) {
+                                   int32_t* nrows_out_dev, int32_t* overflow_dev, int n_runs, int word_bits,
+                                   int lvl_bits, void* stream) {
   QMC_REQUIRE(idx_rows_dev && lvl_rows_dev && row_off_dev && stream_off_dev && words_out_dev && nrows_out_dev &&
               overflow_dev, "null argument");
   QMC_REQUIRE(B > 0 && K > 0 && K <= 256 && IJ > 0 && n_sub > 0, "bad sizes (K must be <= 256)");
   QMC_REQUIRE(tile_warps > 0 && n_sub % tile_warps == 0 && sub_pixels > 0, "bad tiling");
   QMC_REQUIRE((int64_t)tile_warps * sub_pixels + 32 <= 32768, "tile of %lld pixels does not fit the 15-bit pixel field",
               (long long)tile_warps * sub_pixels);
+  QMC_REQUIRE(word_bits == 16 || word_bits == 32, "word_bits must be 16 or 32");
+  QMC_REQUIRE(word_bits == 32 || (lvl_bits >= 1 && lvl_bits <= 8 && (int64_t)tile_warps * sub_pixels <= (1LL << (15 - lvl_bits))),
+              "16-bit words cannot hold %d level bits and a tile of %lld pixels", lvl_bits, (long long)tile_warps * sub_pixels);
+  QMC_REQUIRE(n_runs >= (K + 31) / 32 && n_runs <= 64, "n_runs %d: need at least ceil(K/32) run-table entries per lane", n_runs);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_streams = (int64_t)B * n_sub;
   const int warps = 4;
@@ -538,7 +572,7 @@ extern "C" int qmc_obs_build_lanes(int32_t* idx_rows_dev, uint8_t* lvl_rows_dev,
   obs_lanes_kernel<GG><<<(unsigned)blocks, warps * 32, smem, st>>>(idx_rows_dev, lvl_rows_dev, row_off_dev,     \
                                                                    n_streams, K, IJ, n_sub, sub_pixels, tile_warps, \
                                                                    stream_off_dev, words_out_dev, nrows_out_dev,   \
-                                                                   overflow_dev)
+                                                                   overflow_dev, n_runs, word_bits == 16, lvl_bits)
   switch (G) {
     case 1: QMC_LANES_GO(1); break;
     case 2: QMC_LANES_GO(2); break;

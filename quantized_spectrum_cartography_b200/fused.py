@@ -252,7 +252,8 @@ def make_obs(Y, Wx, K: Optional[int] = None, device=None, *, B: int = 1, R: Opti
             raise ValueError("tiled layout needs R")
         if lanes is None:
             lanes = 32 <= K <= 256          # every lane of the warp owns at least one band
-        n_sub, sub, tw = plan_tiles(IJ, K, R, tile_warps, lanes=lanes)
+        max_level = int(Y.max().item()) if lanes else None      # decides the width of the stream words
+        n_sub, sub, tw = plan_tiles(IJ, K, R, tile_warps, lanes=lanes, max_level=max_level)
         bm = 0 if lanes else bank_mod_for_rank(R)
     else:
         n_sub, sub, tw, bm, lanes = 1, IJ, 0, 0, False

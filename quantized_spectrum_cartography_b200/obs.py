@@ -20,33 +20,54 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def plan_tiles(IJ: int, K: int, R: int, tile_warps: int = 8, smem_budget: int = 110 * 1024, lanes: bool = False):
-    """Choose the pixel sub-tile size for the shared-memory (tiled) kernel.
+def plan_tiles(IJ: int, K: int, R: int, tile_warps: int = 8, smem_budget: int = 110 * 1024, lanes: bool = False,
+               max_level: "int | None" = None):
+    """Choose the pixel sub-tile size for the shared-memory (tiled / lane-stream) kernels.
 
     Returns (n_sub, sub_pixels, tile_warps).  A tile is ``tile_warps`` sub-tiles; its S and gS
     slices ([pixels][R] fp32 each) plus C and gC must fit ``smem_budget`` bytes.  A map that fits
-    in one tile gets exactly one (no cross-CTA reduction of gC at all)."""
+    in one tile gets exactly one (no cross-CTA reduction of gC at all).  ``max_level`` (lane-stream layout):
+    the largest level of the data, which decides whether the compact 16-bit stream words -- and their smaller
+    ring -- can be used (default: plan for 32-bit words)."""
     RP = 1
     while RP < R:
         RP *= 2
-    if lanes:
-        # the lanes kernel always keeps one private gC copy per warp: use fewer warps if K*R is large
-        while tile_warps > 1 and (1 + tile_warps) * (K + 1) * RP * 4 > smem_budget // 2:
-            tile_warps //= 2
-        wc = tile_warps
-        fixed = (1 + wc) * (K + 1) * RP * 4 + tile_warps * 4 * 512 + 16      # C, gC copies, stream rings
-    else:
+
+    def plan(fixed, cap_pixels=None):
+        max_tile_pixels = max((smem_budget - fixed) // (2 * RP * 4), tile_warps)
+        if cap_pixels is not None:
+            max_tile_pixels = min(max_tile_pixels, cap_pixels)
+        if IJ <= max_tile_pixels:
+            return tile_warps, -(-IJ // tile_warps), tile_warps
+        sub = max(max_tile_pixels // tile_warps, 1)
+        tiles = -(-IJ // (sub * tile_warps))
+        return tiles * tile_warps, -(-IJ // (tiles * tile_warps)), tile_warps      # tiles evened out
+
+    if not lanes:
         wc = tile_warps if tile_warps * K * RP * 4 <= 32 * 1024 else 1     # private gC copies (qmc_gather.cu)
-        fixed = (1 + wc) * K * RP * 4 + tile_warps * (K + 2) * 4 + tile_warps * 32 * RP * 4 + 16
-    max_tile_pixels = max((smem_budget - fixed) // (2 * RP * 4), tile_warps)
-    if IJ <= max_tile_pixels:
-        sub = -(-IJ // tile_warps)
-        return tile_warps, sub, tile_warps
-    sub = max(max_tile_pixels // tile_warps, 1)
-    tiles = -(-IJ // (sub * tile_warps))
-    # even the tiles out
-    sub = -(-IJ // (tiles * tile_warps))
-    return tiles * tile_warps, sub, tile_warps
+        return plan((1 + wc) * K * RP * 4 + tile_warps * (K + 2) * 4 + tile_warps * 32 * RP * 4 + 16)
+    # the lanes kernel always keeps one private gC copy per warp (K band rows + dummy + 32 continuation rows):
+    # use fewer warps if K*R is large
+    while tile_warps > 1 and (1 + tile_warps) * (K + 33) * RP * 4 > smem_budget // 2:
+        tile_warps //= 2
+    n_runs = lane_run_entries(K)
+
+    def fixed(ring_bytes):     # C, gC copies, run tables, stream rings (lanes_layout, qmc_gather_common.cuh)
+        return ((K + 1) + tile_warps * (K + 33)) * RP * 4 + tile_warps * (n_runs * 128 + ring_bytes) + 64
+
+    if max_level is not None:
+        lvl_bits = max(1, int(max_level).bit_length())
+        if lvl_bits <= 8:
+            n_sub, sub, tw = plan(fixed(2 * 512), cap_pixels=1 << (15 - lvl_bits))
+            if sub * tw <= (1 << (15 - lvl_bits)):
+                return n_sub, sub, tw
+    return plan(fixed(4 * 512), cap_pixels=32768 - 32)
+
+
+def lane_run_entries(K: int) -> int:
+    """Run-table entries per lane of the lane-stream layout: a lane's quota of groups spans at most
+    ceil(K/32) + 1 bands in the common case; two more entries for uneven band sizes and the final padding run."""
+    return (K + 31) // 32 + 3
 
 
 @dataclass
@@ -67,6 +88,10 @@ class ObsSet:
     stream_off: "torch.Tensor | None" = None   # lane-stream layout: int64 [B*n_sub + 1] word offsets
     nrows: "torch.Tensor | None" = None        # lane-stream layout: int32 [B*n_sub] steps per stream
     stream_stride: int = 0                     # lane-stream layout: > 0 when every stream has the same capacity
+    n_runs: int = 0                            # lane-stream layout: run-table entries per lane
+    word_bits: int = 32                        # lane-stream layout: 16 or 32
+    lvl_bits: int = 0                          # lane-stream layout, 16-bit words: width of the level field
+    has_cont: int = 0                          # lane-stream layout: bands split over lanes (continuation rows)
 
     @property
     def lanes(self) -> bool:
@@ -78,7 +103,8 @@ class ObsSet:
                        self.words.data_ptr() if self.lanes else None,
                        self.stream_off.data_ptr() if self.lanes else None,
                        self.nrows.data_ptr() if self.lanes else None,
-                       self.stream_stride if self.lanes else 0)
+                       self.stream_stride if self.lanes else 0,
+                       self.n_runs, self.word_bits, self.lvl_bits, self.has_cont)
 
     def padding_fraction(self) -> float:
         """Lane-stream layout: fraction of the walked slots that are padding."""
@@ -90,6 +116,44 @@ class ObsSet:
     @property
     def device(self):
         return self.idx.device
+
+    def decode_stream(self, s: int):
+        """Lane-stream layout, for tests and debugging: stream ``s`` as numpy arrays ``[step][lane]`` of
+        (level, band, tile-local pixel, real, gC row) decoded from the run table and the words
+        (include/qmc_b200.h).  ``real`` is False for padding."""
+        import numpy as np
+        if not self.lanes:
+            raise ValueError("not a lane-stream observation set")
+        base = s * self.stream_stride if self.stream_stride > 0 else int(self.stream_off[s].item())
+        steps = int(self.nrows[s].item())
+        ngroups = steps // 4
+        nslots = -(-ngroups // 2) if self.word_bits == 16 else ngroups
+        raw = self.words[base: base + self.n_runs * 32 + nslots * 128].cpu().numpy().view(np.uint32).astype(np.int64)
+        table = raw[: self.n_runs * 32].reshape(self.n_runs, 32)
+        band = np.full((ngroups, 32), self.K, dtype=np.int64)
+        row = np.full((ngroups, 32), self.K, dtype=np.int64)
+        for lane in range(32):
+            g = 0
+            for e in table[:, lane]:
+                n = int(e >> 18)
+                band[g: g + n, lane] = (e >> 9) & 0x1FF
+                row[g: g + n, lane] = e & 0x1FF
+                g += n
+                if g >= ngroups:
+                    break
+            assert g >= ngroups, "run table shorter than the stream"
+        body = raw[self.n_runs * 32:]
+        if self.word_bits == 16:
+            h = body.astype(np.uint32).view(np.uint16).astype(np.int64).reshape(nslots, 32, 2, 4)   # [slot][lane][group][step]
+            w = h.transpose(0, 2, 3, 1).reshape(nslots * 8, 32)[:steps]
+            lb = self.lvl_bits
+            lv, pad, pix = w >> (16 - lb), (w >> (15 - lb)) & 1, w & ((1 << (15 - lb)) - 1)
+            real = pad == 0
+        else:
+            w = body.reshape(nslots, 32, 4).transpose(0, 2, 1).reshape(nslots * 4, 32)[:steps]
+            lv, pix = (((w >> 24) & 0x7F) << 1) | (w >> 31), w & 0x7FFF
+            real = lv != 0xFF
+        return lv, np.repeat(band, 4, axis=0), pix, real, np.repeat(row, 4, axis=0)
 
     def counts_per_map(self) -> torch.Tensor:
         ro = self.row_off[:: self.n_sub * self.K]
@@ -146,6 +210,15 @@ def build_obs(Y: torch.Tensor, Wx: torch.Tensor | None, K: int, IJ: int, B: int 
     return lane_streams(obs) if lanes else obs
 
 
+def lane_word_format(max_level: int, tile_pixels: int) -> "tuple[int, int]":
+    """(word_bits, lvl_bits) of the lane-stream words: 16-bit words when the level field, the padding flag and
+    the tile-local pixel fit, 32-bit words otherwise (include/qmc_b200.h)."""
+    lvl_bits = max(1, int(max_level).bit_length())
+    if lvl_bits <= 8 and tile_pixels <= (1 << (15 - lvl_bits)):
+        return 16, lvl_bits
+    return 32, 0
+
+
 def lane_streams(obs: ObsSet) -> ObsSet:
     """Re-cut a row-ordered observation set (built with ``bank_mod=0``) into the lane-stream layout
     (see qmc_obs_build_lanes): every lane of a stream's warp walks one band at a time and the 32 entries
@@ -160,6 +233,9 @@ def lane_streams(obs: ObsSet) -> ObsSet:
     n_streams = obs.B * obs.n_sub
     per_stream = obs.row_off[:: obs.K][1:] - obs.row_off[:: obs.K][:-1]
     G = (obs.K + 31) // 32
+    word_bits, lvl_bits = lane_word_format(obs.max_level, obs.tile_warps * obs.sub_pixels)
+    n_runs = lane_run_entries(obs.K)
+    steps_per_slot = 8 if word_bits == 16 else 4          # a slot = 32 lanes x 16 bytes = 128 words
     with torch.cuda.device(dev):
         nrows = torch.empty(n_streams, dtype=torch.int32, device=dev)
         overflow = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -168,18 +244,20 @@ def lane_streams(obs: ObsSet) -> ObsSet:
         for attempt in range(4):
             slack = 13 << attempt
             rows_cap = (slack * per_stream * G) // (10 * obs.K) + 4 * G + 8
-            rows_cap = torch.clamp(((rows_cap + 3) // 4) * 4, min=16)     # the kernel loads the first four groups blindly
+            rows_cap = torch.clamp(rows_cap, min=16)              # the kernel loads its first four groups blindly
+            slots = int(-(-int(rows_cap.max().item()) // steps_per_slot)) if n_streams else 4
             # one capacity for all streams (the largest): a stream's address then needs no table look-up, and
             # a CTA can prefetch the data of the CTA that will follow it on its SM
-            stride = int(rows_cap.max().item()) * 32 if n_streams else 512
+            stride = n_runs * 32 + slots * 128
             stream_off = torch.arange(n_streams + 1, dtype=torch.int64, device=dev) * stride
             words = torch.empty(max(n_streams * stride, 1), dtype=torch.int32, device=dev)
             check(lib.qmc_obs_build_lanes(obs.idx.data_ptr(), obs.lvl.data_ptr(), obs.row_off.data_ptr(), obs.B, obs.K,
                                           obs.IJ, obs.n_sub, obs.sub_pixels, obs.tile_warps, stream_off.data_ptr(),
-                                          words.data_ptr(), nrows.data_ptr(), overflow.data_ptr(), _stream()))
+                                          words.data_ptr(), nrows.data_ptr(), overflow.data_ptr(), n_runs, word_bits,
+                                          lvl_bits, _stream()))
             if not int(overflow.item()):
                 break
         else:
             raise RuntimeError("lane-stream layout: a stream exceeded 8x its expected length (pathological band/pixel structure)")
     return ObsSet(obs.idx, obs.lvl, obs.row_off, obs.B, obs.K, obs.IJ, obs.n_sub, obs.sub_pixels, obs.tile_warps,
-                  obs.nobs, obs.max_level, words, stream_off, nrows, stride)
+                  obs.nobs, obs.max_level, words, stream_off, nrows, stride, n_runs, word_bits, lvl_bits, 0)

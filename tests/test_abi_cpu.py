@@ -94,14 +94,16 @@ def test_plan_tiles_covers_the_map():
         assert n_sub % tw == 0 and n_sub * sub >= IJ
         assert (n_sub - tw) * sub < IJ or n_sub == tw      # no entirely empty trailing tile
     assert plan_tiles(2601, 64, 4) == (8, 326, 8)          # cfg1/cfg3: one CTA per map
-    assert plan_tiles(2601, 64, 4, lanes=True) == (8, 326, 8)
+    assert plan_tiles(2601, 64, 4, lanes=True, max_level=1) == (8, 326, 8)   # 16-bit stream words: small ring
+    assert plan_tiles(2601, 64, 4, lanes=True) == (16, 163, 8)               # 32-bit words: two tiles per map
 
 
 def test_lanes_tile_of_cfg3_leaves_room_for_two_ctas_per_sm():
     """Lane-stream kernel at cfg1/cfg3: stream ring + S and gS tiles + C + 8 private gC copies; two CTAs
     (plus 1 KB reserved each) must fit the 228 KB of an SM."""
     from quantized_spectrum_cartography_b200 import _lib
-    b = _lib.lib.qmc_lanes_smem_bytes(64, 4, 326, 8)
-    assert b == (8 * 4 * 32 * 4 + 2 * 326 * 8 * 4 + 65 * 4 + 8 * 65 * 4) * 4 + 16
+    b = _lib.lib.qmc_lanes_smem_bytes(64, 4, 326, 8, 5, 16)
+    # S and gS tiles | C (K+1 rows) | 8 gC copies of K+1+32 rows | run tables (5 entries per lane) | rings (2 slots)
+    assert b == (2 * 326 * 8 * 4 + 65 * 4 + 8 * (65 + 32) * 4 + 8 * 5 * 32 + 8 * 2 * 128) * 4 + 16
     assert 2 * (b + 1024 + 512) <= 228 * 1024
-    assert _lib.lib.qmc_lanes_smem_bytes(64, 4, 100000, 8) == 0
+    assert _lib.lib.qmc_lanes_smem_bytes(64, 4, 100000, 8, 5, 16) == 0

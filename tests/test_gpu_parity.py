@@ -664,8 +664,9 @@ def test_fused_solver_matches_torch_solver(q, K, tiled, pixel_major, graph):
 ])
 def test_lane_stream_builder_and_kernel(q, B, I, J, K, R, levels, log_domain, f, tw, n_tiles):
     """The lane-stream observation layout: (a) the real entries of a step have pairwise distinct
-    pixels, every lane walks its bands as contiguous runs, a band belongs to one lane of the stream,
-    a lane changes band only at group boundaries, padding is level 0xFF, and the entries are exactly those of (Y, Wx);
+    pixels, every lane walks a list of runs (one band per lane and group, from the run table), a gC row is written
+    by one run only (the band's own row by the piece that starts the band, a continuation row by the first run of a
+    lane), padding is flagged, and the entries are exactly those of (Y, Wx);
     (b) the lanes kernel agrees with the oracle and with the flat kernel."""
     from quantized_spectrum_cartography_b200 import _lib
     IJ = I * J
@@ -677,25 +678,28 @@ def test_lane_stream_builder_and_kernel(q, B, I, J, K, R, levels, log_domain, f,
     TP = tw * sub
     obs = q.build_obs(Y.cuda(), Wx.cuda(), K, IJ, B, n_sub=n_sub, sub_pixels=sub, tile_warps=tw, lanes=True)
     assert obs.lanes and obs.nobs == int(Wx.sum().item())
-    words = obs.words.cpu().numpy().view(np.uint32).astype(np.int64)
+    from quantized_spectrum_cartography_b200.obs import lane_word_format
+    assert (obs.word_bits, obs.lvl_bits) == lane_word_format(obs.max_level, TP)
     so = obs.stream_off.cpu().numpy()
     nr = obs.nrows.cpu().numpy()
     seen = []
     for s_id in range(B * n_sub):
         b, st = divmod(s_id, n_sub)
         p0 = (st // tw) * TP
-        assert nr[s_id] % 4 == 0 and so[s_id] % 128 == 0
-        blk = words[so[s_id]: so[s_id] + 32 * nr[s_id]].reshape(-1, 32, 4).transpose(0, 2, 1).reshape(-1, 32)   # [step][lane]
-        lv, band, pix = (((blk >> 24) & 0x7F) << 1) | (blk >> 31), (blk >> 15) & 0x1FF, blk & 0x7FFF
-        real = lv != 0xFF
-        g4 = band.reshape(-1, 4, 32)
-        assert np.all(g4 == g4[:, :1, :])                                                # one band per lane and group
-        owner = {}
+        assert nr[s_id] % 4 == 0 and so[s_id] % 32 == 0
+        lv, band, pix, real, row = obs.decode_stream(s_id)                              # [step][lane]
+        assert np.all(band[real] < K)
+        writers = {}
         for lane in range(32):
-            runs = band[:, lane][np.r_[True, band[1:, lane] != band[:-1, lane]]] if len(band) else []
-            assert len(set(runs.tolist() if len(band) else [])) == len(runs)            # contiguous runs
-            for k in set(band[real[:, lane], lane].tolist()):
-                assert owner.setdefault(k, lane) == lane                                 # one lane per band
+            chg = np.r_[True, (band[1:, lane] != band[:-1, lane]) | (row[1:, lane] != row[:-1, lane])] if len(band) else []
+            for i, t in enumerate(np.nonzero(chg)[0] if len(band) else []):
+                assert t % 4 == 0                                                        # runs start at group boundaries
+                r_, k_ = int(row[t, lane]), int(band[t, lane])
+                if r_ == K:
+                    assert not real[t:, lane][band[t:, lane] == k_].any() or k_ == K     # dummy row: nothing real
+                    continue
+                assert r_ == k_ or (r_ == K + 1 + lane and i == 0)                       # own row, or continuation as first run
+                assert writers.setdefault(r_, (lane, int(t))) == (lane, int(t))          # one run per gC row
         for row_real, row_pix in zip(real, pix):
             v = row_pix[row_real]
             assert len(set(v.tolist())) == len(v)
