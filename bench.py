@@ -156,12 +156,52 @@ def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_bud
                 thr=thr, sigma=sigma)
 
 
+def config_keys(n_maps_per_gpu: int):
+    """The `config` keys both arms print (the b200 arm adds its layout details)."""
+    c = CFG3
+    IJ, K, R = c["I"] * c["J"], c["K"], c["R"]
+    gb = n_maps_per_gpu * (c["sampling"] * K * IJ * 5 + 2 * 4 * R * (IJ + K) + 4) / 1e9    # SURVEY 8(d), expected value
+    return {"workload": c["workload"], "maps_per_gpu": n_maps_per_gpu, "shape": "51x51x64", "rank": c["R"],
+            "sampling": c["sampling"], "levels": c["levels"], "evaluation_point": "0.8*S_true, C_true",
+            "l2": "inputs ~%.2f GB/step per GPU > 126 MB L2 (no flush needed)" % gb}
+
+
+def load_reference():
+    """The reference's own implementation of the path: oracle/_ref/quantization_model.py, copied verbatim from
+    /root/reference/qmc by oracle/make_ref.py in the build container (kind "reference"); the oracle's port of it
+    when that copy is missing (kind "port").  Test infrastructure: only the CPU legs of this file use it."""
+    import importlib.util
+    path = os.path.join(ROOT, "oracle", "_ref", "quantization_model.py")
+    if os.path.exists(path):
+        spec = importlib.util.spec_from_file_location("reference_quantization_model", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod, "reference"
+    from oracle import qmc_oracle as oc
+    return oc, "port"
+
+
+def reference_evaluation(mod, kind, S, Cm, Y, Wx, bb, sigma, vectorised=False):
+    """One evaluation the way the reference does it (qmc/qmc.ipynb c1:145-153 with the functions of
+    qmc/quantization_model.py:22-39,57-61,70-86): NLL forward + autograd backward to S and C.  Returns the NLL."""
+    import torch
+    if kind == "port" or vectorised:
+        from oracle import qmc_oracle as oc
+        return oc.nll_and_grads(S, Cm, Y, Wx, bb, sigma, vectorised=vectorised)[0]
+    S = S.clone().requires_grad_(True)
+    Cm = Cm.clone().requires_grad_(True)
+    T_hat = mod.get_tensor(S, Cm).unsqueeze(dim=1)
+    nll = -torch.sum(Wx * torch.log(mod.prob_probit(Y, T_hat, bb, sigma)))
+    nll.backward()
+    return nll.detach()
+
+
 def cpu_reference_sample(hs, I, J, K, R, budget_s: float, vectorised: bool = False, max_maps: int = 256):
-    """Time the oracle's torch-CPU port of the reference algorithm (get_tensor -> prob_probit ->
-    -sum(Wx*log P) -> backward) map by map until the budget is spent.  Returns (obs/s, maps, seconds)."""
+    """Time the reference's CPU implementation of the path (get_tensor -> prob_probit -> -sum(Wx*log P) -> backward)
+    map by map until the budget is spent.  Returns (obs/s, maps, seconds, kind)."""
     import torch
 
-    from oracle import qmc_oracle as oc
+    mod, kind = load_reference()
     torch.set_num_threads(os.cpu_count() or 1)
     n_obs, t_used, done = 0, 0.0, 0
     n_avail = min(max_maps, hs["S"].shape[0])
@@ -172,44 +212,66 @@ def cpu_reference_sample(hs, I, J, K, R, budget_s: float, vectorised: bool = Fal
         Y = hs["Y"][b].reshape(K, 1, I, J).long()
         Wx = hs["Wx"][b].reshape(K, 1, I, J)
         t0 = time.perf_counter()
-        nll, gS, gC = oc.nll_and_grads(S, Cm, Y, Wx, hs["bb"], hs["sigma"], vectorised=vectorised)
+        nll = reference_evaluation(mod, kind, S, Cm, Y, Wx, hs["bb"], hs["sigma"], vectorised=vectorised)
         t_used += time.perf_counter() - t0
         assert torch.isfinite(nll), "reference NLL is not finite on the benchmark workload"
         n_obs += int(Wx.sum().item())
         done += 1
-    return n_obs / t_used, done, t_used
+    return n_obs / t_used, done, t_used, kind
+
+
+def cpu_workload_slice(n_maps: int, seed: int = 0):
+    """The first maps of the cfg3 workload synthesised on the host cores alone: same generator code
+    (quantized_spectrum_cartography_b200/synth.py, loaded by path: it needs torch only, not the CUDA library), same
+    quantizer semantics through the oracle.  Nothing of the product is imported."""
+    import importlib.util
+
+    import torch
+
+    from oracle import qmc_oracle as oc
+    spec = importlib.util.spec_from_file_location("qmc_synth_cpu", os.path.join(ROOT, "quantized_spectrum_cartography_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec)
+    sys.modules["qmc_synth_cpu"] = synth          # dataclasses look the defining module up
+    spec.loader.exec_module(synth)
+    c = CFG3
+    I, J, K, R = c["I"], c["J"], c["K"], c["R"]
+    maps = synth.generate_maps(n_maps, I, J, K, R, seed=seed, device="cpu")
+    T = maps.tensor()
+    thr = T.reshape(-1)[:: max(1, T.numel() // 2_000_000)].median().item()
+    sigma = thr
+    bb = torch.tensor([0.0, thr, 1.0])
+    gen = torch.Generator().manual_seed(seed + 1)
+    noisy = oc.noisy_signal(T, torch.randn(T.shape, generator=gen), sigma)
+    Y = oc.assign_levels(noisy, bb)
+    Wx = torch.bernoulli(torch.full(T.shape, c["sampling"]), generator=gen)
+    return dict(Y=Y, Wx=Wx, S=(0.8 * maps.S_true).contiguous(), C=maps.C_true.contiguous(), bb=bb, sigma=sigma)
 
 
 # -------------------------------------------------------------------------------------------------
 def run_reference(args, rank: int, world: int):
-    """--impl reference: the reference's own CPU algorithm (oracle port; the reference is Python and
-    /root/reference does not exist on the GPU box) on this box's host cores.  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref, the verbatim modules;
+    the oracle port if they are missing) on this box's host cores, on a slice of the same workload synthesised on
+    the CPU.  Does not import the product and needs no GPU.  Rank 0 only."""
     if rank != 0:
         return
     import torch
 
-    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
     c = CFG3
-    # a 256-map slice of the same workload is all the CPU arm ever touches
-    if dev.type == "cuda":
-        wl = build_workload(256, dev, seed=0)
-        hs = wl["host_sample"]
-    else:
-        raise SystemExit(json.dumps({"impl": "reference", "unavailable": "no CUDA device to synthesise the workload"}))
-    maps_per_step = 8
-    per_step = []
-    n_obs_step = []
-    torch.set_num_threads(os.cpu_count() or 1)
-    from oracle import qmc_oracle as oc
     I, J, K, R = c["I"], c["J"], c["K"], c["R"]
+    maps_per_step = 8
+    n_slice = min(256, maps_per_step * (args.steps + args.warmup))
+    hs = cpu_workload_slice(n_slice, seed=0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    mod, kind = load_reference()
 
     def step(i):
         tot = 0
         for b in range(maps_per_step):
             m = (i * maps_per_step + b) % hs["S"].shape[0]
             Wx = hs["Wx"][m].reshape(K, 1, I, J)
-            oc.nll_and_grads(hs["S"][m].reshape(R, 1, I, J), hs["C"][m], hs["Y"][m].reshape(K, 1, I, J).long(), Wx,
-                             hs["bb"], hs["sigma"])
+            nll = reference_evaluation(mod, kind, hs["S"][m].reshape(R, 1, I, J), hs["C"][m], hs["Y"][m].reshape(K, 1, I, J), Wx,
+                                       hs["bb"], hs["sigma"])
+            assert torch.isfinite(nll)
             tot += int(Wx.sum().item())
         return tot
 
@@ -222,15 +284,13 @@ def run_reference(args, rank: int, world: int):
     dt = time.perf_counter() - t0
     value = total / dt
     cores = torch.get_num_threads()
-    sample = f"{maps_per_step} of {c['maps']} maps per step, {args.steps} steps"
+    sample = f"{maps_per_step} of {c['maps']} maps per step, {args.steps} steps, maps synthesised on the host"
     print(json.dumps({
         "impl": "reference", "metric": "QMC observed-entries/s (fused NLL fwd + gS + gC)", "value": value,
         "unit": "observed-entries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": c["workload"], "maps_per_gpu": c["maps"], "shape": "51x51x64", "rank": c["R"],
-                   "sampling": c["sampling"], "levels": c["levels"]},
-        "cpu_baseline": {"value": value, "unit": "observed-entries/s", "cores": cores, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": config_keys(args.maps),
+        "cpu_baseline": {"value": value, "unit": "observed-entries/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "observed-entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -379,11 +439,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
-        v, nmaps, secs = cpu_reference_sample(wl["host_sample"], wl["I"], wl["J"], K, R, args.cpu_seconds)
-        vf, nmaps_f, secs_f = cpu_reference_sample(wl["host_sample"], wl["I"], wl["J"], K, R,
-                                                   min(4.0, args.cpu_seconds), vectorised=True)
+        v, nmaps, secs, kind = cpu_reference_sample(wl["host_sample"], wl["I"], wl["J"], K, R, args.cpu_seconds)
+        vf, nmaps_f, secs_f, _ = cpu_reference_sample(wl["host_sample"], wl["I"], wl["J"], K, R,
+                                                      min(4.0, args.cpu_seconds), vectorised=True)
         import torch as _t
-        cpu = {"value": v, "unit": "observed-entries/s", "cores": _t.get_num_threads(), "kind": "port",
+        cpu = {"value": v, "unit": "observed-entries/s", "cores": _t.get_num_threads(), "kind": kind,
                "sample": f"{nmaps} map evaluations (fwd+bwd) cycling over the first 256 of {B} maps, {secs:.1f} s of CPU work",
                "value_vectorised_fair_cpu": vf}
 
@@ -392,11 +452,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         "metric": "QMC observed-entries/s (fused NLL fwd + gS + gC)", "value": value, "unit": "observed-entries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": c["workload"], "maps_per_gpu": B, "shape": "51x51x64", "rank": R,
-                   "sampling": c["sampling"], "levels": c["levels"], "observed_entries_per_gpu": obs.nobs,
-                   "S_layout": args.layout, "tile_warps": obs.tile_warps, "tiles_per_map": obs.n_sub // obs.tile_warps,
-                   "obs_layout": "lanes" if obs.lanes else "rows", "obs_padding": round(obs.padding_fraction(), 4), "l2": "inputs %.2f GB/step per GPU > 126 MB L2 (no flush needed)" % (alg_bytes / 1e9),
-                   "evaluation_point": "0.8*S_true, C_true", "threshold": wl["thr"], "sigma": wl["sigma"]},
+        "config": config_keys(B),
+        "layout": {"observed_entries_per_gpu": obs.nobs, "S_layout": args.layout, "tile_warps": obs.tile_warps,
+                   "tiles_per_map": obs.n_sub // obs.tile_warps, "obs_layout": "lanes" if obs.lanes else "rows",
+                   "obs_word_bits": obs.word_bits if obs.lanes else None, "obs_padding": round(obs.padding_fraction(), 4),
+                   "threshold": wl["thr"], "sigma": wl["sigma"]},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "solver": solver,
         "evaluations_per_s": args.steps / (total_ms * 1e-3) * world,
     }

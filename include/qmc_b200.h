@@ -162,17 +162,20 @@ QMC_API int qmc_obs_fill(const void* y_dev, int y_is_int64, const float* wx_dev,
                  int32_t* idx_out_dev, uint8_t* lvl_out_dev, void* stream);
 
 /* Re-cut a row-ordered observation set (n_sub, sub_pixels as built by qmc_obs_count_scan/qmc_obs_fill
- * with bank_mod = 0) into the lane-stream layout for tiles of tile_warps sub-tiles.  idx_rows/lvl_rows
- * are used as scratch and come back permuted inside their rows.  stream_off_dev: caller-chosen
- * capacities in words (multiples of 128; 32 * (1.3 * n * G / K + 4 * G + 8) words, G = ceil(K/32), for a stream of n
- * entries is ample); nrows_out_dev receives the steps actually used; *overflow_dev is set to 1 if a
- * stream did not fit its capacity.  Every stream must have room for at least 16 steps (the kernel loads
- * its first four groups before it knows the length).  K <= 256, levels <= 254,
- * tile_warps * sub_pixels + 32 <= 32768. */
-QMC_API int qmc_obs_build_lanes(int32_t* idx_rows_dev, uint8_t* lvl_rows_dev, const int64_t* row_off_dev,
+ * with bank_mod = 0; read only) into the lane-stream layout for tiles of tile_warps sub-tiles: per stream the
+ * bands are laid end to end in 4-step groups and cut into 32 equal quotas, one per lane (see qmc_obs_view_t and
+ * csrc/qmc_lanes_build.cu).  Every stream occupies stream_stride 32-bit words of words_out_dev (a multiple of 32,
+ * at least qmc_lanes_stream_words(max_entries_per_stream, K, n_runs, word_bits, extra_groups));
+ * nrows_out_dev receives the steps actually used.  *overflow_dev comes back non-zero if some stream could not be
+ * laid out: bits 0, 2, 3 = not every entry found a slot (capacity / too many short pieces / repair failed: retry
+ * with more extra_groups), bit 1 = a lane needs more than n_runs - 1 runs (retry with a larger n_runs).  K <= 256, levels <= 254, tile_warps * sub_pixels + 32 <= 32768;
+ * word_bits == 16 needs lvl_bits + 1 + ceil(log2(tile pixels)) <= 16. */
+QMC_API int64_t qmc_lanes_stream_words(int64_t max_entries_per_stream, int K, int n_runs, int word_bits, int extra_groups);
+QMC_API int qmc_obs_build_lanes(const int32_t* idx_rows_dev, const uint8_t* lvl_rows_dev, const int64_t* row_off_dev,
                         int B, int K, int IJ, int n_sub, int sub_pixels, int tile_warps,
-                        const int64_t* stream_off_dev, uint32_t* words_out_dev, int32_t* nrows_out_dev,
-                        int32_t* overflow_dev, int n_runs, int word_bits, int lvl_bits, void* stream);
+                        int64_t max_entries_per_stream, int extra_groups, int split_bands, int64_t stream_stride,
+                        uint32_t* words_out_dev, int32_t* nrows_out_dev, int32_t* overflow_dev, int n_runs,
+                        int word_bits, int lvl_bits, void* stream);
 /* Shared-memory bytes of the lanes kernel for a geometry (0 if it cannot run it). */
 QMC_API int64_t qmc_lanes_smem_bytes(int K, int R, int sub_pixels, int tile_warps, int n_runs, int word_bits);
 

@@ -50,7 +50,8 @@ SIGNATURES = {
     "qmc_obs_scan_ws_elems": (_L, [_L]),
     "qmc_obs_count_scan": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "qmc_obs_fill": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "qmc_obs_build_lanes": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "qmc_lanes_stream_words": (_L, [_L, _I, _I, _I, _I]),
+    "qmc_obs_build_lanes": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _I, _I, _L, _P, _P, _P, _I, _I, _I, _P]),
     "qmc_lanes_smem_bytes": (_L, [_I, _I, _I, _I, _I, _I]),
     "qmc_sumsq_per_map": (_I, [_P, _I, _L, _P, _P]),
     "qmc_adam_frob_project": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _F, _F, _F, _F, _F, _I, _I, _P, _P]),

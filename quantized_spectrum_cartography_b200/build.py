@@ -24,7 +24,8 @@ COMMON_DEPS = ["qmc_common.cuh", "erfcx_coeffs.h", os.path.join("..", "..", "inc
 
 def units() -> list[tuple[str, str, list[str], list[str]]]:
     u = [("qmc_abi.cu", "qmc_abi", [], []), ("qmc_quantize.cu", "qmc_quantize", [], []),
-         ("qmc_dense.cu", "qmc_dense", [], []), ("qmc_solver.cu", "qmc_solver", [], []), ("qmc_gather.cu", "qmc_gather", [], ["qmc_gather_common.cuh"])]
+         ("qmc_dense.cu", "qmc_dense", [], []), ("qmc_solver.cu", "qmc_solver", [], []), ("qmc_gather.cu", "qmc_gather", [], ["qmc_gather_common.cuh"]),
+         ("qmc_lanes_build.cu", "qmc_lanes_build", [], ["qmc_gather_common.cuh"])]
     for fam, name in FAMILIES.items():
         for rp in RANKS:
             u.append(("qmc_gather_inst.cu", f"qmc_gather_{name}_r{rp}", [f"-DQMC_FAMILY={fam}", f"-DQMC_RP={rp}"],

@@ -2,6 +2,7 @@
 //   qmc_noisy_signal    : quantization_model.py:13 / quantization_model_log.py:14
 //   qmc_quantize_levels : quantization_model.py:14-20 (bit-exact level assignment)
 //   qmc_obs_count_scan / qmc_obs_fill : (Y, Wx) dense [B][K][IJ] -> (idx, lvl, row_off)
+// (the lane-stream builder lives in qmc_lanes_build.cu)
 #include "qmc_common.cuh"
 
 namespace qmc {
@@ -145,297 +146,6 @@ __global__ void obs_fill_kernel(const YT* __restrict__ y, const float* __restric
   }
 }
 
-// ---- lane streams -------------------------------------------------------------------------------
-// One warp per (map, sub-tile) stream.  The stream's rows (bands) are dealt to the 32 lanes in snake
-// order of their sizes (largest, ..., 32nd | 64th, ..., 33rd | ...), so every lane owns about the same
-// number of entries, and a lane walks its bands one after the other: in the gather kernel the lane
-// keeps C[band] and the band's gC accumulator in registers.  Step t of the stream takes one entry
-// from every lane; the entries of a step have pairwise distinct pixels (hard: the kernel updates gS
-// rows without atomics) and, where the lane still has a choice, distinct shared-memory bank groups
-// inside each quarter-warp (soft).  A lane that cannot comply, or has nothing left, emits a padding
-// word; a lane changes band only at a multiple of four steps.  Word: bit 31 = level & 1, bits 24..30 =
-// level >> 1, bits 15..23 = band, bits 0..14 = tile-local pixel; padding has bits 24..31 all set (level
-// 0xFF) and carries the lane's current band.  Steps are stored in groups of four, lane-interleaved:
-// word(t, lane) at ((t / 4) * 32 + lane) * 4 + t % 4.
-constexpr int LANE_GROUP = 4;
-constexpr uint32_t LANE_PAD_LEVEL = 0xFFu;
-
-// Bank-group assignment inside one quarter-warp: lane i may take bank group r (pixel row mod 8) if it
-// still has a candidate pixel in that group (byte r of cnt[i] > 0).  Maximum bipartite matching by
-// augmenting paths (8 x 8), each lane trying its best-stocked groups first so that the groups it keeps
-// for later steps stay diverse.  owner[r] = lane of the quarter that takes group r, or -1.
-__device__ bool lanes_augment(int i, const unsigned long long* cnt, int* owner, unsigned& visited) {
-  unsigned cand = 0;
-#pragma unroll
-  for (int r = 0; r < 8; ++r)
-    if ((cnt[i] >> (8 * r)) & 0xFFull) cand |= 1u << r;
-  cand &= ~visited;
-  while (cand) {
-    int best = 0, bc = -1;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int cr = (int)((cnt[i] >> (8 * r)) & 0xFFull);
-      if (((cand >> r) & 1u) && cr > bc) { bc = cr; best = r; }
-    }
-    cand &= ~(1u << best);
-    visited |= 1u << best;
-    if (owner[best] < 0 || lanes_augment(owner[best], cnt, owner, visited)) {
-      owner[best] = i;
-      return true;
-    }
-  }
-  return false;
-}
-
-template <int G>
-__global__ void obs_lanes_kernel(int32_t* __restrict__ idx, uint8_t* __restrict__ lvl,
-                                 const int64_t* __restrict__ row_off, int64_t n_streams, int K, int IJ, int n_sub,
-                                 int sub_pixels, int tile_warps, const int64_t* __restrict__ stream_off,
-                                 uint32_t* __restrict__ words, int32_t* __restrict__ nrows,
-                                 int32_t* __restrict__ overflow, int n_runs, int word16, int lvl_bits) {
-  extern __shared__ __align__(16) unsigned char lanes_smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (s >= n_streams) return;
-  // per warp: hist[32][G] u64 | band_of_rank[K16] i16 | lane_bands[32][G] i16 | assign[32] i16
-  const int K16 = (K + 15) & ~15;
-  const size_t per_warp = (size_t)32 * G * 8 + (size_t)K16 * 2 + (size_t)32 * G * 2 + 64;
-  unsigned char* wbase = lanes_smem + wib * per_warp;
-  unsigned long long* sh_hist = reinterpret_cast<unsigned long long*>(wbase);
-  int16_t* band_of_rank = reinterpret_cast<int16_t*>(wbase + (size_t)32 * G * 8);
-  int16_t* sh_bands = band_of_rank + K16;
-  int16_t* sh_assign = sh_bands + 32 * G;
-  const int64_t row0 = s * K;
-  const int64_t beg = row_off[row0];
-  const int st = (int)(s % n_sub);
-  const int TP = tile_warps * sub_pixels;
-  const int p0 = (st / tile_warps) * TP;  // first pixel of the tile this sub-tile belongs to
-  const uint32_t own0 = (uint32_t)((st % tile_warps) * sub_pixels);  // tile-local: first pixel of this sub-tile (idle padding points here)
-  // rank the bands by size (descending, ties by band index)
-  for (int k = lane; k < K; k += 32) {
-    const int64_t ck = row_off[row0 + k + 1] - row_off[row0 + k];
-    int rank = 0;
-    for (int j = 0; j < K; ++j) {
-      const int64_t cj = row_off[row0 + j + 1] - row_off[row0 + j];
-      rank += (cj > ck) || (cj == ck && j < k);
-    }
-    band_of_rank[rank] = (int16_t)k;
-  }
-  __syncwarp();
-  int bands[G];
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    const int r = (g & 1) ? 32 * g + 31 - lane : 32 * g + lane;
-    bands[g] = r < K ? band_of_rank[r] : -1;
-  }
-  // Regroup the 32 band sets into the four quarter-warps so that, phase by phase (g-th band of every
-  // lane), each quarter's supply of pixels per shared-memory bank group is as even as possible: a
-  // quarter-warp can avoid bank conflicts only while all eight groups are still in stock.
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    unsigned long long h = 0;
-    if (bands[g] >= 0) {
-      const int c0 = (int)(row_off[row0 + bands[g]] - beg), e0 = (int)(row_off[row0 + bands[g] + 1] - beg);
-      for (int qq = c0; qq < e0; ++qq) {
-        const int r = (idx[beg + qq] - bands[g] * IJ - p0) & 7;
-        if (((h >> (8 * r)) & 0xFFull) < 255) h += 1ull << (8 * r);
-      }
-    }
-    sh_hist[lane * G + g] = h;
-  }
-  __syncwarp();
-  {
-    const int myq = lane >> 3, myr = lane & 7;  // this lane keeps the running supply of (quarter, bank group)
-    int supply[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) supply[g] = 0;
-    int fill = 0;  // lanes already placed in this lane's quarter
-    for (int i = 0; i < 32; ++i) {
-      int add[G];
-      int cost = 0;
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        add[g] = (int)((sh_hist[i * G + g] >> (8 * myr)) & 0xFFull);
-        int mx = supply[g] + add[g], mn = mx;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        }
-        cost += mx - mn;
-      }
-      if (fill >= 8) cost = 0x3fffffff;
-      int best = 0, bc = 0x7fffffff;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int ck = __shfl_sync(0xffffffffu, cost, 8 * k);
-        if (ck < bc) { bc = ck; best = k; }
-      }
-      const int slot = __shfl_sync(0xffffffffu, fill, 8 * best);
-      if (myq == best) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) supply[g] += add[g];
-        ++fill;
-      }
-      if (lane == 0) sh_assign[i] = (int16_t)(8 * best + slot);
-    }
-  }
-  __syncwarp();
-  {
-    const int dst = sh_assign[lane];
-#pragma unroll
-    for (int g = 0; g < G; ++g) sh_bands[dst * G + g] = (int16_t)bands[g];
-  }
-  __syncwarp();
-  int left = 0;  // entries this lane still has to emit
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    bands[g] = sh_bands[lane * G + g];
-    if (bands[g] >= 0) left += (int)(row_off[row0 + bands[g] + 1] - row_off[row0 + bands[g]]);
-  }
-  int g = -1, band = K, cur = 0, end = 0;  // band K: the dummy band of a lane that owns nothing
-  unsigned long long cnt = 0;              // candidates left per bank group, for band cnt_band
-  int cnt_band = -1;
-  // stream: run table (n_runs entries per lane, [entry][lane]) followed by the words in 512-byte slots
-  // (32 lanes x 16 bytes: four 32-bit words = one group, or eight 16-bit words = two groups)
-  uint32_t* const table = words + stream_off[s];
-  const int64_t out0 = stream_off[s] + (int64_t)n_runs * 32;
-  const int cap = (int)((stream_off[s + 1] - out0) >> 7) * (word16 ? 8 : 4);  // steps
-  uint16_t* const words16 = reinterpret_cast<uint16_t*>(words + out0);
-  auto put_word = [&](int t, uint32_t lv, bool pad, uint32_t pix) {
-    const int gi = t >> 2;
-    if (word16) {
-      const uint32_t lvf = pad ? ((1u << lvl_bits) - 1u) : lv;  // padding: all level bits set (the one-bit epilogue relies on it)
-      words16[((int64_t)(gi >> 1) * 32 + lane) * 8 + (gi & 1) * 4 + (t & 3)] =
-          (uint16_t)((lvf << (16 - lvl_bits)) | ((pad ? 1u : 0u) << (15 - lvl_bits)) | pix);
-    } else {
-      const uint32_t lvf = pad ? LANE_PAD_LEVEL : lv;
-      words[out0 + ((int64_t)gi * 32 + lane) * LANE_GROUP + (t & 3)] = ((lvf & 1u) << 31) | ((lvf >> 1) << 24) | pix;
-    }
-  };
-  int nrun = 0, run_band = -1, run_beg = 0;  // run table of this lane
-  for (int i = 0; i < n_runs; ++i) table[i * 32 + lane] = 0u;
-  int step = 0;
-  while (__any_sync(0xffffffffu, left > 0)) {
-    // move on to the lane's next non-empty band -- only at a group boundary, so that the gather
-    // kernel sees one band per lane and group
-    if ((step & (LANE_GROUP - 1)) == 0) {
-      while (cur >= end && g < G) {
-        ++g;
-        int nb = -1;
-#pragma unroll
-        for (int gg = 0; gg < G; ++gg)
-          if (gg == g) nb = bands[gg];
-        if (g < G && nb >= 0) {
-          const int c0 = (int)(row_off[row0 + nb] - beg), e0 = (int)(row_off[row0 + nb + 1] - beg);
-          if (e0 > c0) { band = nb; cur = c0; end = e0; }
-        }
-      }
-      if (band != run_band) {  // a new run: close the previous entry, open the next
-        if (nrun > 0 && nrun <= n_runs)
-          table[(nrun - 1) * 32 + lane] = (uint32_t)run_band | ((uint32_t)run_band << 9) | ((uint32_t)((step >> 2) - run_beg) << 18);
-        run_band = band;
-        run_beg = step >> 2;
-        ++nrun;
-      }
-    }
-    const bool has = cur < end;
-    // per-bank-group counts of the lane's remaining candidates (8 x 8 bits, saturating at 255; a
-    // saturated field is recounted after the next take)
-    if (has && cnt_band != band) {
-      cnt = 0;
-      for (int qq = cur; qq < end; ++qq) {
-        const int r = (idx[beg + qq] - band * IJ - p0) & 7;
-        if (((cnt >> (8 * r)) & 0xFFull) < 255) cnt += 1ull << (8 * r);
-      }
-      cnt_band = band;
-    }
-    // matching of the quarter-warp's lanes to bank groups (every lane of the quarter computes the same)
-    unsigned long long qc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) qc[i] = __shfl_sync(0xffffffffu, has ? cnt : 0ull, (lane & 24) + i);
-    int owner[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) owner[r] = -1;
-    for (int i = 0; i < 8; ++i) {
-      unsigned visited = 0;
-      if (qc[i]) lanes_augment(i, qc, owner, visited);
-    }
-    int want = -1;  // the bank group this lane should use in this step
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-      if (owner[r] == (lane & 7)) want = r;
-    // pick a pixel: pass 0 walks the candidates of group `want`, pass 1 any candidate; a candidate is
-    // taken if no other lane of the warp holds the same pixel (hard)
-    bool active = has, won = false;
-    int pass = want >= 0 ? 0 : 1, q = cur - 1, id = 0, pix = -(lane + 2);
-    auto advance = [&]() {  // next candidate of the current pass, or give up
-      while (active) {
-        ++q;
-        if (q >= end) {
-          if (pass == 1) { active = false; pix = -(lane + 2); break; }
-          pass = 1;
-          q = cur - 1;
-          continue;
-        }
-        id = idx[beg + q];
-        pix = id - band * IJ - p0;
-        if (pass == 1 || (pix & 7) == want) break;
-      }
-    };
-    advance();
-    for (int it = 0; it < 4 * 96; ++it) {
-      const unsigned wonmask = __ballot_sync(0xffffffffu, won);
-      const unsigned und = __ballot_sync(0xffffffffu, active && !won);
-      if (!und) break;
-      const unsigned m = __match_any_sync(0xffffffffu, pix);
-      if (active && !won) {
-        if ((m & wonmask) == 0 && lane == __ffs(m & und) - 1) won = true;
-        else advance();
-      }
-    }
-    if (!won) pix = -(lane + 2);
-    // padding re-reads the S row of a real lane of the same quarter-warp (same address: no extra
-    // shared-memory wavefront); its updates are predicated off in the kernel
-    const unsigned wonmask = __ballot_sync(0xffffffffu, won);
-    const unsigned wonq = wonmask & (0xffu << (lane & 24));
-    const int srcl = wonq ? __ffs(wonq) - 1 : (wonmask ? __ffs(wonmask) - 1 : lane);
-    const int padpix = __shfl_sync(0xffffffffu, pix, srcl);
-    int lvw = 0;
-    if (won) {
-      const int lv = lvl[beg + q];
-      if (q != cur) {  // move the chosen entry to the front of what is left of the row
-        idx[beg + q] = idx[beg + cur];
-        lvl[beg + q] = lvl[beg + cur];
-        idx[beg + cur] = id;
-        lvl[beg + cur] = (uint8_t)lv;
-      }
-      ++cur;
-      --left;
-      if (((cnt >> (8 * (pix & 7))) & 0xFFull) == 255) cnt_band = -1;  // saturated: recount
-      else cnt -= 1ull << (8 * (pix & 7));
-      lvw = lv;
-    }
-    if (step < cap) put_word(step, (uint32_t)lvw, !won, won ? (uint32_t)pix : (wonmask ? (uint32_t)padpix : own0));
-    ++step;
-    if (step > cap + 4096) break;  // hopeless: report and stop
-  }
-  // pad the last group; idle padding points at the first pixel of the stream's own sub-tile (rows the warp itself staged)
-  while (step & (LANE_GROUP - 1)) {
-    if (step < cap) put_word(step, 0u, true, own0);
-    ++step;
-  }
-  // the last run never ends (a lane that has run out keeps walking padding words of its last band); a lane
-  // that never opened a run walks the dummy band K
-  if (nrun == 0) { run_band = K; nrun = 1; }
-  if (nrun <= n_runs) table[(nrun - 1) * 32 + lane] = (uint32_t)run_band | ((uint32_t)run_band << 9) | (0x3FFFu << 18);
-  const bool bad_runs = __any_sync(0xffffffffu, nrun > n_runs);
-  if (lane == 0) {
-    nrows[s] = step <= cap ? step : cap;
-    if (step > cap || bad_runs) atomicExch(overflow, 1);
-  }
-}
-
 // ---- exclusive scan of int64 counts (in place: counts[i] -> offset, plus total at [n]) ----------
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -539,51 +249,6 @@ extern "C" int qmc_quantize_levels(const float* noisy_dev, int64_t n, const floa
   tab.n = n_bounds;
   for (int i = 0; i < n_bounds; ++i) tab.b[i] = bounds_host[i];
   quantize_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(noisy_dev, n, tab, lvl_out_dev, y_out_dev);
-  count_launch();
-  QMC_CUDA_CHECK(cudaGetLastError());
-  return QMC_OK;
-}
-
-extern "C" int qmc_obs_build_lanes(int32_t* idx_rows_dev, uint8_t* lvl_rows_dev, const int64_t* row_off_dev,
-                                   int B, int K, int IJ, int n_sub, int sub_pixels, int tile_warps,
-                                   const int64_t* stream_off_dev, uint32_t* words_out_dev,
-                                   int32_t* nrows_out_dev, int32_t* overflow_dev, int n_runs, int word_bits,
-                                   int lvl_bits, void* stream) {
-  QMC_REQUIRE(idx_rows_dev && lvl_rows_dev && row_off_dev && stream_off_dev && words_out_dev && nrows_out_dev &&
-              overflow_dev, "null argument");
-  QMC_REQUIRE(B > 0 && K > 0 && K <= 256 && IJ > 0 && n_sub > 0, "bad sizes (K must be <= 256)");
-  QMC_REQUIRE(tile_warps > 0 && n_sub % tile_warps == 0 && sub_pixels > 0, "bad tiling");
-  QMC_REQUIRE((int64_t)tile_warps * sub_pixels + 32 <= 32768, "tile of %lld pixels does not fit the 15-bit pixel field",
-              (long long)tile_warps * sub_pixels);
-  QMC_REQUIRE(word_bits == 16 || word_bits == 32, "word_bits must be 16 or 32");
-  QMC_REQUIRE(word_bits == 32 || (lvl_bits >= 1 && lvl_bits <= 8 && (int64_t)tile_warps * sub_pixels <= (1LL << (15 - lvl_bits))),
-              "16-bit words cannot hold %d level bits and a tile of %lld pixels", lvl_bits, (long long)tile_warps * sub_pixels);
-  QMC_REQUIRE(n_runs >= (K + 31) / 32 && n_runs <= 64, "n_runs %d: need at least ceil(K/32) run-table entries per lane", n_runs);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t n_streams = (int64_t)B * n_sub;
-  const int warps = 4;
-  const int64_t blocks = (n_streams + warps - 1) / warps;
-  QMC_REQUIRE(blocks <= 0x7fffffff, "too many streams");
-  QMC_CUDA_CHECK(cudaMemsetAsync(overflow_dev, 0, sizeof(int32_t), st));
-  const int G = (K + 31) / 32;
-  const int Gt = G > 8 ? 8 : G;
-  const size_t smem = (size_t)warps * ((size_t)32 * Gt * 8 + (size_t)((K + 15) & ~15) * 2 + (size_t)32 * Gt * 2 + 64);
-#define QMC_LANES_GO(GG)                                                                                       \
-  obs_lanes_kernel<GG><<<(unsigned)blocks, warps * 32, smem, st>>>(idx_rows_dev, lvl_rows_dev, row_off_dev,     \
-                                                                   n_streams, K, IJ, n_sub, sub_pixels, tile_warps, \
-                                                                   stream_off_dev, words_out_dev, nrows_out_dev,   \
-                                                                   overflow_dev, n_runs, word_bits == 16, lvl_bits)
-  switch (G) {
-    case 1: QMC_LANES_GO(1); break;
-    case 2: QMC_LANES_GO(2); break;
-    case 3: QMC_LANES_GO(3); break;
-    case 4: QMC_LANES_GO(4); break;
-    case 5: QMC_LANES_GO(5); break;
-    case 6: QMC_LANES_GO(6); break;
-    case 7: QMC_LANES_GO(7); break;
-    default: QMC_LANES_GO(8); break;
-  }
-#undef QMC_LANES_GO
   count_launch();
   QMC_CUDA_CHECK(cudaGetLastError());
   return QMC_OK;

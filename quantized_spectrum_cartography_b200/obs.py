@@ -8,6 +8,7 @@ builds, once per instance, a list of observed entries -- a 4-byte linear index `
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -66,8 +67,9 @@ def plan_tiles(IJ: int, K: int, R: int, tile_warps: int = 8, smem_budget: int = 
 
 def lane_run_entries(K: int) -> int:
     """Run-table entries per lane of the lane-stream layout: a lane's quota of groups spans at most
-    ceil(K/32) + 1 bands in the common case; two more entries for uneven band sizes and the final padding run."""
-    return (K + 31) // 32 + 3
+    ceil(K/32) + 1 bands when the bands are of similar size; three more entries for uneven band sizes (the builder
+    reports a lane that needs more and the caller retries with a longer table)."""
+    return (K + 31) // 32 + 4
 
 
 @dataclass
@@ -221,8 +223,8 @@ def lane_word_format(max_level: int, tile_pixels: int) -> "tuple[int, int]":
 
 def lane_streams(obs: ObsSet) -> ObsSet:
     """Re-cut a row-ordered observation set (built with ``bank_mod=0``) into the lane-stream layout
-    (see qmc_obs_build_lanes): every lane of a stream's warp walks one band at a time and the 32 entries
-    of a step hit 32 different pixels.  The row-ordered arrays are consumed (permuted in place)."""
+    (see qmc_obs_build_lanes): every lane of a stream's warp walks a list of (band, groups) runs, all lanes
+    of a stream get the same number of groups, and the 32 entries of a step hit 32 different pixels."""
     if obs.K > 256:
         raise ValueError("the lane-stream layout supports at most 256 bands")
     if obs.max_level > 254:
@@ -232,32 +234,36 @@ def lane_streams(obs: ObsSet) -> ObsSet:
     dev = obs.device
     n_streams = obs.B * obs.n_sub
     per_stream = obs.row_off[:: obs.K][1:] - obs.row_off[:: obs.K][:-1]
-    G = (obs.K + 31) // 32
+    e_max = int(per_stream.max().item()) if n_streams else 0
     word_bits, lvl_bits = lane_word_format(obs.max_level, obs.tile_warps * obs.sub_pixels)
     n_runs = lane_run_entries(obs.K)
-    steps_per_slot = 8 if word_bits == 16 else 4          # a slot = 32 lanes x 16 bytes = 128 words
+    extra = int(os.environ.get("QMC_LANES_EXTRA", "0"))
+    split = int(os.environ.get("QMC_LANES_SPLIT", "1"))
     with torch.cuda.device(dev):
         nrows = torch.empty(n_streams, dtype=torch.int32, device=dev)
         overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        # capacity: 1.3x the even share of the busiest lane; dense sampling of small sub-tiles (every band
-        # wants the same few pixels in the same step) can need more -> retry with twice the room
-        for attempt in range(4):
-            slack = 13 << attempt
-            rows_cap = (slack * per_stream * G) // (10 * obs.K) + 4 * G + 8
-            rows_cap = torch.clamp(rows_cap, min=16)              # the kernel loads its first four groups blindly
-            slots = int(-(-int(rows_cap.max().item()) // steps_per_slot)) if n_streams else 4
-            # one capacity for all streams (the largest): a stream's address then needs no table look-up, and
-            # a CTA can prefetch the data of the CTA that will follow it on its SM
-            stride = n_runs * 32 + slots * 128
-            stream_off = torch.arange(n_streams + 1, dtype=torch.int64, device=dev) * stride
+        for attempt in range(12):
+            # one capacity for all streams (that of the largest): a stream's address then needs no table look-up,
+            # and a CTA can prefetch the data of the CTA that will follow it on its SM
+            stride = int(lib.qmc_lanes_stream_words(e_max, obs.K, n_runs, word_bits, extra))
             words = torch.empty(max(n_streams * stride, 1), dtype=torch.int32, device=dev)
             check(lib.qmc_obs_build_lanes(obs.idx.data_ptr(), obs.lvl.data_ptr(), obs.row_off.data_ptr(), obs.B, obs.K,
-                                          obs.IJ, obs.n_sub, obs.sub_pixels, obs.tile_warps, stream_off.data_ptr(),
+                                          obs.IJ, obs.n_sub, obs.sub_pixels, obs.tile_warps, e_max, extra, split, stride,
                                           words.data_ptr(), nrows.data_ptr(), overflow.data_ptr(), n_runs, word_bits,
                                           lvl_bits, _stream()))
-            if not int(overflow.item()):
+            ov = int(overflow.item())
+            if not ov:
                 break
+            # dense sampling of small sub-tiles (every band wants the same few pixels in the same step) needs room
+            # to spread out; many tiny bands per quota need a longer run table
+            if os.environ.get("QMC_DEBUG_LANES"):
+                print(f"lane_streams: attempt {attempt} overflow bits {ov:#x} (extra {extra}, n_runs {n_runs})")
+            if ov & 13:
+                extra = max(1, 2 * extra)
+            if ov & 2:
+                n_runs = min(64, n_runs + 4)
         else:
-            raise RuntimeError("lane-stream layout: a stream exceeded 8x its expected length (pathological band/pixel structure)")
+            raise RuntimeError("lane-stream layout: could not lay the observations out (pathological band/pixel structure)")
+    stream_off = torch.arange(n_streams + 1, dtype=torch.int64, device=dev) * stride
     return ObsSet(obs.idx, obs.lvl, obs.row_off, obs.B, obs.K, obs.IJ, obs.n_sub, obs.sub_pixels, obs.tile_warps,
-                  obs.nobs, obs.max_level, words, stream_off, nrows, stride, n_runs, word_bits, lvl_bits, 0)
+                  obs.nobs, obs.max_level, words, stream_off, nrows, stride, n_runs, word_bits, lvl_bits, int(split != 0))

@@ -657,7 +657,7 @@ def test_fused_solver_matches_torch_solver(q, K, tiled, pixel_major, graph):
     (5, 51, 51, 64, 4, 2, False, 0.10, 8, 1),      # cfg1/cfg3 geometry
     (3, 30, 31, 40, 3, 4, True, 0.30, 4, 2),       # K not a multiple of 32, two tiles per map, padded rank
     (2, 40, 40, 128, 8, 8, True, 0.20, 8, 1),      # cfg2-like
-    (1, 64, 64, 256, 16, 8, False, 0.50, 2, 4),    # cfg4-like bands and rank
+    (1, 64, 64, 256, 16, 8, False, 0.50, 4, 8),    # cfg4-like bands and rank
     (4, 23, 17, 33, 1, 2, False, 0.60, 2, 1),      # rank 1, dense sampling
     (2, 19, 21, 12, 2, 2, False, 0.40, 4, 1),      # fewer bands than lanes: idle lanes walk the dummy band
     (3, 51, 51, 64, 4, 2, False, 0.01, 8, 1),      # very sparse: bands of 0..3 entries, many band switches per group
