@@ -161,6 +161,22 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   // the first copies need not know its length.
   const uint32_t hdr_a = smem_u32(smem + L.hdr) + (uint32_t)(warp * prm.n_runs * 32 + lane) * 4u;
   const uint32_t ring_a = smem_u32(smem + L.ring) + (uint32_t)((warp * SLOTS) * 32 + lane) * 16u;
+  if (!bulk) {
+    // emitter-major storage (the reference's [R][IJ]): the slice is transposed into [p][r] rows by 4-byte
+    // asynchronous copies, all in flight at once and in a cp.async group of their own, older than the ring's.  RP
+    // consecutive lanes take the RP emitters of one pixel: the shared-memory side of a copy is 32 consecutive
+    // words (no bank conflict), the global side RP runs of 32/RP consecutive pixels.
+    constexpr int PPI = RP <= 32 ? 32 / RP : 1;  // pixels per copy instruction
+    const int r = lane % RP, pq = lane / RP;
+    const uint32_t Sw_a = smem_u32(Sw);
+    const float* src = Sb + (int64_t)r * prm.sR + (int64_t)(p0 + sl0) * prm.sP;
+    if (r < prm.R) {
+      for (int pl = pq; pl < sln; pl += PPI) cp_async4(Sw_a + (uint32_t)(pl * RP + r) * 4u, src + (int64_t)pl * prm.sP);
+    } else {
+      for (int pl = pq; pl < sln; pl += PPI) Sw[pl * RP + r] = 0.0f;  // padded rank
+    }
+    cp_async_commit();
+  }
   for (int i = 0; i < prm.n_runs; ++i) cp_async4(hdr_a + i * 128, sbase + i * 32 + lane);
 #pragma unroll
   for (int d = 0; d < SLOTS; ++d) {
@@ -208,36 +224,6 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       prefetch_l2(v2 + o);
     }
   }
-  if (!bulk) {
-    // emitter-major storage (the reference's): every lane gathers the R values of one pixel with coalesced
-    // row reads and writes them as one row [p][0..RP) -- the transposition happens in registers; the loads
-    // of SU pixels per lane are all in flight before the first store waits for one
-    constexpr int SU = RP <= 8 ? 4 : 1;
-    for (int i0 = 0; i0 < sln; i0 += 32 * SU) {
-      float tmp[SU][RP];
-#pragma unroll
-      for (int u = 0; u < SU; ++u) {
-        const int pl = i0 + u * 32 + lane;
-#pragma unroll
-        for (int r = 0; r < RP; ++r)
-          tmp[u][r] = (pl < sln && r < prm.R) ? __ldg(Sb + r * prm.sR + (int64_t)(p0 + sl0 + pl) * prm.sP) : 0.0f;
-      }
-#pragma unroll
-      for (int u = 0; u < SU; ++u) {
-        const int pl = i0 + u * 32 + lane;
-        if (pl < sln) {
-          if (RP % 4 == 0) {
-#pragma unroll
-            for (int r = 0; r < RP; r += 4)
-              *reinterpret_cast<float4*>(Sw + pl * RP + r) = make_float4(tmp[u][r], tmp[u][r + 1], tmp[u][r + 2], tmp[u][r + 3]);
-          } else {
-#pragma unroll
-            for (int r = 0; r < RP; ++r) Sw[pl * RP + r] = tmp[u][r];
-          }
-        }
-      }
-    }
-  }
   if (GRAD) {
     float* zc = gCw + (size_t)warp * (K + XROWS) * RP;
     if (RP % 4 == 0) {
@@ -262,6 +248,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   const int ngroups = nrows_v >> 2;
   __syncthreads();  // Csm and `done` are ready; the slices are private to their warps
   if (use_bar) mbar_wait(&mbar[warp], 0);
+  if (!bulk) cp_async_wait<SLOTS>();  // the S slice (every group but the ring's SLOTS newest)
   __syncwarp();
 
   constexpr uint32_t ROWB = RP * sizeof(float);
@@ -585,23 +572,16 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       __syncwarp();
       if (lane == 0) bulk_s2g(gSb + (int64_t)(p0 + sl0) * RP, gSw, (uint32_t)sln * RP * sizeof(float));
     } else {
-      // emitter-major: one 16-byte row read per lane and pixel, R coalesced row writes
+      // emitter-major: RP consecutive lanes take the RP emitters of one pixel -- conflict-free 4-byte reads of
+      // the tile, R runs of consecutive pixels per store instruction
       __syncwarp();
-      for (int pl = lane; pl < sln; pl += 32) {
-        float row[RP];
-        if (RP % 4 == 0) {
-#pragma unroll
-          for (int r = 0; r < RP; r += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(gSw + pl * RP + r);
-            row[r] = v.x; row[r + 1] = v.y; row[r + 2] = v.z; row[r + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < RP; ++r) row[r] = gSw[pl * RP + r];
-        }
-#pragma unroll
-        for (int r = 0; r < RP; ++r)
-          if (r < prm.R) gSb[r * prm.sR + (int64_t)(p0 + sl0 + pl) * prm.sP] = row[r];
+      constexpr int PPI = RP <= 32 ? 32 / RP : 1;
+      const int r = lane % RP, pq = lane / RP;
+      if (r < prm.R) {
+        float* dst = gSb + (int64_t)r * prm.sR + (int64_t)(p0 + sl0 + pq) * prm.sP;
+        const int64_t dstep = (int64_t)PPI * prm.sP;
+        const float* srcp = gSw + pq * RP + r;
+        for (int pl = pq; pl < sln; pl += PPI, dst += dstep, srcp += PPI * RP) *dst = *srcp;
       }
     }
   }
