@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-solver", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling, cfg4 (dense / sharded) and emitter-major records")
     ap.add_argument("--tile-warps", type=int, default=8)
     ap.add_argument("--smem-budget-kb", type=int, default=110)
     ap.add_argument("--obs-layout", default="lanes", choices=["lanes", "rows"],
@@ -295,6 +296,131 @@ def run_reference(args, rank: int, world: int):
     }))
 
 
+def _timed(fn, n, stream, barrier):
+    """Mean device time of fn() in ms over n calls, max over ranks taken by the caller."""
+    import torch
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(n):
+        fn()
+    b.record(stream)
+    barrier()
+    return a.elapsed_time(b) / n
+
+
+def strong_scaling_record(args, rank, world, dev, barrier, reduce_max, reduce_sum):
+    """BASELINE configs[2] as written: 4096 maps in TOTAL, partitioned over the ranks by parallel.partition_maps /
+    BatchedMaps, no collective on the data path.  One evaluation per step, replayed from a CUDA graph (at 8 GPUs a
+    step is ~30 us of kernel: the Python call would be as long)."""
+    import torch
+
+    import quantized_spectrum_cartography_b200 as q
+    from quantized_spectrum_cartography_b200 import parallel
+    total = CFG3["maps"]
+    lo, hi = parallel.partition_maps(total, world, rank)
+    n = hi - lo
+    wl = build_workload(n, dev, seed=100 + rank)
+    bm = parallel.BatchedMaps(lo, hi, total, wl["obs"], wl["lik"])
+    S = wl["S"].transpose(1, 2).contiguous().transpose(1, 2)
+    Cf = wl["C"]
+    out = (torch.empty(n, dtype=torch.float64, device=dev), torch.empty_strided(S.shape, S.stride(), dtype=torch.float32, device=dev),
+           torch.empty_like(Cf))
+    stream = torch.cuda.current_stream()
+    for _ in range(3):
+        bm.evaluate(S, Cf, out=out)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        bm.evaluate(S, Cf, out=out)
+    for _ in range(args.warmup):
+        g.replay()
+    cap = torch.cuda.current_stream()
+    ms = reduce_max(_timed(g.replay, args.steps, cap, barrier))
+    nobs = reduce_sum(float(wl["obs"].nobs))
+    ctas = n * (wl["obs"].n_sub // wl["obs"].tile_warps)
+    slots = 2 * torch.cuda.get_device_properties(dev).multi_processor_count
+    waves = ctas / slots
+    return {"maps_total": total, "maps_per_gpu": n, "ms_per_step": ms, "value": nobs / (ms * 1e-3), "unit": "observed-entries/s",
+            "ctas_per_gpu": ctas, "resident_ctas_per_gpu": slots, "waves": round(waves, 3),
+            "wave_quantisation_ceiling": round(waves / -(-ctas // slots), 3), "collective": "none",
+            "api": "parallel.BatchedMaps.evaluate (one CUDA graph replay per step)"}
+
+
+def cfg4_record(args, rank, world, dev, barrier, reduce_max):
+    """BASELINE configs[3]: one 512x512x256 instance, R = 16, 50 % sampling, 8 levels, log domain -- the dense
+    tcgen05 kernel on this rank's pixel block (parallel.ShardedInstance; the whole instance at one GPU) and,
+    at N > 1, the NCCL all-reduce of the factor gradients: the contract form ("flat": [gS|gC|nll], 16.8 MB) and the
+    pixel-block form ([gC|nll] only).  Per mode: time of one evaluation (local kernel + collective, one CUDA graph),
+    of the local part alone and of the collective alone."""
+    import torch
+    import torch.distributed as dist
+
+    import quantized_spectrum_cartography_b200 as q
+    from quantized_spectrum_cartography_b200 import dense, parallel, qmc
+    c = qmc.CONFIGS["cfg4"]
+    I, J, K, R = c["I"], c["J"], c["K"], c["R"]
+    IJ = I * J
+    pb = qmc.synth_problem("cfg4", 1, dev, seed=0)          # same seed on every rank: replicated inputs
+    Y, Wx, lik = pb["Y"][0], pb["Wx"][0], pb["lik"]
+    nobs = int(pb["obs"].nobs)
+    S = (0.8 * pb["maps"].S_true[0]).contiguous()
+    Cm = pb["maps"].C_true[0].contiguous()
+    ref = None
+    if world > 1:                                           # single-GPU answer for the error columns
+        d1 = dense.pack_dense(Y, Wx, K)
+        ref = [x.clone() for x in dense.nll_fwd_bwd_dense(S, Cm, d1, lik)]
+        del d1
+    del pb
+    torch.cuda.empty_cache()
+    stream = torch.cuda.current_stream()
+    rec = {"shape": f"{I}x{J}x{K}", "rank": R, "sampling": c["f"], "levels": c["levels"], "log_domain": bool(c["log_domain"]),
+           "observed_entries": nobs, "kernel": "dense_kernel (tcgen05 kind::tf32, 3xTF32)", "modes": {}}
+    n_it = max(args.steps, 10)
+    for mode in (("flat", "pixel_block") if world > 1 else ("pixel_block",)):
+        inst = parallel.ShardedInstance.from_dense(Y, Wx, K, R, lik, mode=mode, align=128, dense=True)
+        Sl = S[:, inst.lo:inst.hi].contiguous()
+        use_graph = True
+        try:
+            inst.evaluate(Sl, Cm, gather_gS=False, cuda_graph=True)
+        except Exception as e:                               # NCCL capture unavailable: time the eager sequence
+            use_graph = False
+            inst._graph = None
+            torch.cuda.synchronize()
+        if use_graph:
+            Sl, Cm_in = inst._S_in, inst._C_in                 # the graph's own input buffers: no staging copy
+        else:
+            Cm_in = Cm
+        ev = lambda: inst.evaluate(Sl, Cm_in, gather_gS=False, cuda_graph=use_graph)
+        for _ in range(3):
+            ev()
+        ms = reduce_max(_timed(lambda: (inst._graph.replay() if use_graph else inst._step(Sl, Cm_in)), n_it, stream, barrier))
+        nll, gS, gC = ev()
+        m = {"ms_per_eval": ms, "entries_per_s": nobs / (ms * 1e-3), "exchange_bytes": inst.exchange_bytes() if world > 1 else 0,
+             "cuda_graph": use_graph, "pixels_per_gpu": inst.hi - inst.lo}
+        off = R * IJ if mode == "flat" else R * (inst.hi - inst.lo)
+        local = lambda: inst._local_into(inst._buf, Sl, Cm_in, off)
+        for _ in range(3):
+            local()
+        m["local_kernel_ms"] = reduce_max(_timed(local, n_it, stream, barrier))
+        if world > 1:
+            coll = (lambda: dist.all_reduce(inst._buf)) if mode == "flat" else (lambda: dist.all_reduce(inst._buf[off:]))
+            for _ in range(3):
+                coll()
+            m["all_reduce_ms"] = reduce_max(_timed(coll, n_it, stream, barrier))
+            nll, gS, gC = inst.evaluate(Sl, Cm_in, gather_gS=False, cuda_graph=use_graph)   # buffers were clobbered by the timing loops
+            gS_ref = ref[1] if mode == "flat" else ref[1][:, inst.lo:inst.hi]
+            m["err_vs_one_gpu"] = {"nll": abs(nll.item() / ref[0].item() - 1), "gS": float((gS - gS_ref).norm() / gS_ref.norm()),
+                                   "gC": float((gC - ref[2]).norm() / ref[2].norm())}
+        rec["modes"][mode] = m
+        del inst
+    d = dense.DenseObs(torch.empty(0), IJ, K, nobs, 0)
+    best = min(v["ms_per_eval"] for v in rec["modes"].values())
+    rec["algorithmic_bytes"] = d.algorithmic_bytes(R)
+    rec["mma_tflops"] = 3 * 2.0 * IJ * K * R / (best * 1e-3) / 1e12
+    return rec
+
+
 def run_b200(args, rank: int, world: int, local_rank: int):
     import ctypes as C
 
@@ -364,6 +490,25 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     nobs_all = n.item()
     value = nobs_all * args.steps / (total_ms * 1e-3)
 
+    # ---- the same step with S in the reference's own layout (emitter-major [R][IJ]) ---------------------------
+    em_ms = None
+    if not args.no_extra and args.layout == "pixel_major":
+        S_em = wl["S"]
+        gS_em = torch.empty_like(S_em)
+
+        def step_em():
+            check(lib.qmc_nll_fwd_bwd_gather(S_em.data_ptr(), S_em.stride(0), S_em.stride(1), S_em.stride(2), Cf.data_ptr(),
+                                             C.byref(view), C.byref(lik), B, IJ, K, R, _lib.QMC_ALGO_AUTO,
+                                             obs.tile_warps, nll.data_ptr(), gS_em.data_ptr(), gC.data_ptr(),
+                                             stream.cuda_stream))
+        for _ in range(args.warmup):
+            step_em()
+        em = torch.tensor([_timed(step_em, args.steps, stream, barrier)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(em, op=dist.ReduceOp.MAX)
+        em_ms = em.item()
+        del gS_em
+
     # ---- end to end through the host-buffer C-ABI call -----------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -414,6 +559,26 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                "Adam, projection, next norm); one CUDA graph replayed",
                   "observed_entries_per_s": 2 * nobs_all * n_it / ts.item()}
 
+    # ---- the two multi-GPU configurations BASELINE.json names, and the dense path ------------------------------
+    def reduce_max(x):
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt.item()
+
+    def reduce_sum(x):
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        return tt.item()
+
+    strong = cfg4 = None
+    if not args.no_extra:
+        del gS, gC, nll
+        torch.cuda.empty_cache()
+        strong = strong_scaling_record(args, rank, world, dev, barrier, reduce_max, reduce_sum) if world > 1 else None
+        cfg4 = cfg4_record(args, rank, world, dev, barrier, reduce_max)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -437,6 +602,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_launch_ms,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
+    roofline_em = None
+    if em_ms is not None:
+        roofline_em = {"bound": "hbm", "achieved": alg_bytes / (em_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": alg_bytes / (em_ms * 1e-3) / 1e9 / peak, "mean_launch_ms": em_ms,
+                       "S_layout": "emitter_major (the reference's [R,1,I,J]; transposed into shared-memory rows by 4-byte asynchronous copies)"}
+
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
         v, nmaps, secs, kind = cpu_reference_sample(wl["host_sample"], wl["I"], wl["J"], K, R, args.cpu_seconds)
@@ -457,7 +628,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                    "tiles_per_map": obs.n_sub // obs.tile_warps, "obs_layout": "lanes" if obs.lanes else "rows",
                    "obs_word_bits": obs.word_bits if obs.lanes else None, "obs_padding": round(obs.padding_fraction(), 4),
                    "threshold": wl["thr"], "sigma": wl["sigma"]},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "solver": solver,
+        "roofline": roofline, "roofline_emitter_major": roofline_em, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "solver": solver, "strong": strong, ("dense_cfg4" if world == 1 else "sharded_cfg4"): cfg4,
         "evaluations_per_s": args.steps / (total_ms * 1e-3) * world,
     }
     print(json.dumps(out))

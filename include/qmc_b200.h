@@ -235,11 +235,13 @@ QMC_API int qmc_dense_pack(const void* y_dev, int y_is_int64, const float* wx_de
 
 /* Same contract as qmc_nll_fwd_bwd_gather for ONE instance (B = 1) with S [R][IJ], C [R][K] contiguous:
  * X = S*C^T, gS = G*C and gC = G^T*S are formed by tcgen05.mma (kind::tf32, 3xTF32 operand split, fp32
- * accumulators in tensor memory); X and G = dNLL/dX never touch HBM.  Supported: K a multiple of 32 and
+ * accumulators in tensor memory); X and G = dNLL/dX never touch HBM.  gs_row_stride: elements between the rows of
+ * gS_out_dev (0 = IJ; larger when the rows are written straight into a wider buffer, e.g. the pixel block of one
+ * rank inside the all-reduce buffer of a sharded instance).  Supported: K a multiple of 32 and
  * <= 256, R <= 16, levels <= 255; otherwise QMC_ERR_UNSUPPORTED (use the gather entry point). */
 QMC_API int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, const uint8_t* code_dev,
                           const qmc_likelihood_t* lik, int IJ, int K, int R, double* nll_out_dev,
-                          float* gS_out_dev, float* gC_out_dev, void* stream);
+                          float* gS_out_dev, int64_t gs_row_stride, float* gC_out_dev, void* stream);
 /* Shared-memory bytes of the dense kernel for a geometry (0 = unsupported). */
 QMC_API int64_t qmc_dense_smem_bytes(int K, int R);
 

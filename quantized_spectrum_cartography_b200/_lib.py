@@ -64,7 +64,7 @@ SIGNATURES = {
     "qmc_nll_fwd_bwd_gather_host": (_I, [_P, _P, _P, _P, C.POINTER(ObsView), C.POINTER(Likelihood),
                                          _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "qmc_dense_pack": (_I, [_P, _I, _P, _I, _I, _I, _P, _P]),
-    "qmc_nll_fwd_bwd_dense": (_I, [_P, _P, _P, C.POINTER(Likelihood), _I, _I, _I, _P, _P, _P, _P]),
+    "qmc_nll_fwd_bwd_dense": (_I, [_P, _P, _P, C.POINTER(Likelihood), _I, _I, _I, _P, _P, _L, _P, _P]),
     "qmc_dense_smem_bytes": (_L, [_I, _I]),
     "qmc_get_tensor": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "qmc_nmse_terms": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),

@@ -35,7 +35,8 @@ struct DenseParams {
   const float* C;        // [R][K]
   const uint8_t* code;   // [IJ][K]
   double* nll;
-  float* gS;             // [R][IJ]
+  float* gS;             // [R][IJ], row stride gs_stride
+  int64_t gs_stride;
   float* gC;             // [R][K]
   int IJ, K, R, Rp8, n_tiles;
   int n_bounds;
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
         if (inside) {
 #pragma unroll
           for (int r = 0; r < 16; ++r)
-            if (r < R) prm.gS[(size_t)r * prm.IJ + p0 + row] = v[r];
+            if (r < R) prm.gS[(size_t)r * prm.gs_stride + p0 + row] = v[r];
         }
       }
     }
@@ -486,9 +487,10 @@ extern "C" int64_t qmc_dense_smem_bytes(int K, int R) {
 
 extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, const uint8_t* code_dev,
                                      const qmc_likelihood_t* lik, int IJ, int K, int R, double* nll_out_dev,
-                                     float* gS_out_dev, float* gC_out_dev, void* stream) {
+                                     float* gS_out_dev, int64_t gs_row_stride, float* gC_out_dev, void* stream) {
   QMC_REQUIRE(S_dev && C_dev && code_dev && lik && nll_out_dev, "null argument");
   QMC_REQUIRE(IJ > 0 && R > 0, "bad sizes");
+  QMC_REQUIRE(gs_row_stride == 0 || gs_row_stride >= IJ, "gs_row_stride %lld is smaller than IJ", (long long)gs_row_stride);
   if (K <= 0 || K > 256 || (K % DT_BLK) != 0)
     return set_error(QMC_ERR_UNSUPPORTED, "dense path needs K a multiple of %d and <= 256 (got %d)", DT_BLK, K);
   if (R > DT_RP) return set_error(QMC_ERR_UNSUPPORTED, "dense path needs rank <= %d (got %d)", DT_RP, R);
@@ -504,6 +506,7 @@ extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, con
 
   DenseParams prm;
   prm.S = S_dev; prm.C = C_dev; prm.code = code_dev; prm.nll = nll_out_dev; prm.gS = gS_out_dev; prm.gC = gC_out_dev;
+  prm.gs_stride = gs_row_stride > 0 ? gs_row_stride : IJ;
   prm.IJ = IJ; prm.K = K; prm.R = R; prm.Rp8 = R <= 8 ? 8 : 16;
   prm.n_tiles = (IJ + DT_PIX - 1) / DT_PIX;
   prm.n_bounds = lik->n_bounds;

@@ -56,8 +56,10 @@ def pack_dense(Y: torch.Tensor, Wx: Optional[torch.Tensor], K: int) -> DenseObs:
     return DenseObs(code, IJ, K, nobs, max_level)
 
 
-def nll_fwd_bwd_dense(S2: torch.Tensor, C2: torch.Tensor, obs: DenseObs, lik: Likelihood, want_grad: bool = True):
-    """``S2 [R, IJ]``, ``C2 [R, K]`` fp32 CUDA.  Returns (nll fp64 0-dim, gS [R, IJ], gC [R, K])."""
+def nll_fwd_bwd_dense(S2: torch.Tensor, C2: torch.Tensor, obs: DenseObs, lik: Likelihood, want_grad: bool = True, out=None):
+    """``S2 [R, IJ]``, ``C2 [R, K]`` fp32 CUDA.  Returns (nll fp64 0-dim, gS [R, IJ], gC [R, K]).
+    ``out=(nll fp64 [1], gS, gC)`` writes into existing buffers; gS may then be a column slice of a wider
+    row-major buffer (row stride >= IJ, unit column stride), gC must be contiguous."""
     if not (S2.is_cuda and C2.is_cuda):
         raise ValueError("nll_fwd_bwd_dense needs CUDA tensors: there is no CPU path")
     R, IJ = S2.shape
@@ -70,10 +72,19 @@ def nll_fwd_bwd_dense(S2: torch.Tensor, C2: torch.Tensor, obs: DenseObs, lik: Li
     C2 = C2.contiguous()
     lik = _with_flags(lik, not want_grad)
     with torch.cuda.device(S2.device):
-        nll = torch.empty(1, dtype=torch.float64, device=S2.device)
-        gS = torch.empty_like(S2) if want_grad else None
-        gC = torch.empty_like(C2) if want_grad else None
+        if out is not None:
+            nll, gS, gC = out
+            if nll.dtype != torch.float64 or nll.numel() < 1:
+                raise ValueError("out[0] must hold one float64")
+            if want_grad and (gS.shape != (R, IJ) or gS.stride(1) != 1 or gS.stride(0) < IJ or gS.dtype != torch.float32
+                              or not gC.is_contiguous() or gC.shape != (R, K)):
+                raise ValueError("out buffers: gS [R, IJ] fp32 with unit column stride, gC [R, K] contiguous")
+        else:
+            nll = torch.empty(1, dtype=torch.float64, device=S2.device)
+            gS = torch.empty_like(S2) if want_grad else None
+            gC = torch.empty_like(C2) if want_grad else None
         check(lib.qmc_nll_fwd_bwd_dense(S2.data_ptr(), C2.data_ptr(), obs.code.data_ptr(), C.byref(lik), IJ, K, R,
                                         nll.data_ptr(), gS.data_ptr() if want_grad else None,
+                                        gS.stride(0) if want_grad else 0,
                                         gC.data_ptr() if want_grad else None, _stream()))
-    return nll[0], gS, gC
+    return nll.reshape(-1)[0], gS, gC

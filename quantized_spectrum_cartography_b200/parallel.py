@@ -13,7 +13,8 @@ Two cases, matching how the path shards:
   the scalar NLL are partial.  Two exchange forms:
 
   - ``"flat"``  -- the contract form BASELINE.json names: one all-reduce (sum, fp32) of the flat
-    ``[gS | gC | nll]`` buffer, 4*(R*IJ + R*K + 1) bytes (16.8 MB at cfg4);
+    ``[gS | gC | nll]`` buffer, 4*(R*IJ + R*K + 2) bytes (16.8 MB at cfg4); the tcgen05 kernel writes its pixel
+    block of gS, its gC and its NLL straight into that persistent buffer;
   - ``"pixel_block"`` -- all-reduce only ``[gC | nll]`` (16 KB at cfg4) and, if the caller wants the
     full gS everywhere, all-gather the disjoint gS slices.
 
@@ -54,14 +55,14 @@ def _world() -> tuple[int, int]:
 # -------------------------------------------------------------------------------------------------
 # batched independent maps: no collective
 # -------------------------------------------------------------------------------------------------
-def _cuda_local_eval(S3, C3, obs, lik, want_grad=True):
+def _cuda_local_eval(S3, C3, obs, lik, want_grad=True, out=None):
     """Product evaluator: the gather kernels for an ObsSet, the tcgen05 kernel for a DenseObs."""
     from .dense import DenseObs, nll_fwd_bwd_dense
     from .fused import nll_fwd_bwd
     if isinstance(obs, DenseObs):
         nll, gS, gC = nll_fwd_bwd_dense(S3[0], C3[0], obs, lik, want_grad=want_grad)
         return nll.reshape(1), None if gS is None else gS.unsqueeze(0), None if gC is None else gC.unsqueeze(0)
-    return nll_fwd_bwd(S3, C3, obs, lik, want_grad=want_grad)
+    return nll_fwd_bwd(S3, C3, obs, lik, want_grad=want_grad, out=out)
 
 
 @dataclass
@@ -90,8 +91,11 @@ class BatchedMaps:
             obs = build(Y, Wx)
         return cls(lo, hi, n_maps, obs, lik, local_eval)
 
-    def evaluate(self, S3, C3, want_grad: bool = True):
-        """NLL ``[hi-lo]`` (fp64), gS, gC of this rank's maps.  No communication."""
+    def evaluate(self, S3, C3, want_grad: bool = True, out=None):
+        """NLL ``[hi-lo]`` (fp64), gS, gC of this rank's maps.  No communication.  ``out=(nll, gS, gC)`` reuses
+        buffers (CUDA evaluator only)."""
+        if out is not None:
+            return self.local_eval(S3, C3, self.obs, self.lik, want_grad, out=out)
         return self.local_eval(S3, C3, self.obs, self.lik, want_grad)
 
     def gather_nll(self, nll_local: torch.Tensor) -> Optional[torch.Tensor]:
@@ -126,6 +130,11 @@ class ShardedInstance:
     mode: str = "flat"
     local_eval: Callable = _cuda_local_eval
     align: int = 1
+    _buf: Optional[torch.Tensor] = None      # persistent exchange buffer (fp32): [gS | gC | nll_hi, nll_lo]
+    _nll64: Optional[torch.Tensor] = None
+    _graph: object = None
+    _S_in: Optional[torch.Tensor] = None     # staging copies of the inputs the captured graph reads
+    _C_in: Optional[torch.Tensor] = None
 
     @classmethod
     def from_dense(cls, Y, Wx, K: int, R: int, lik, *, mode: str = "flat", device=None, align: int = 1,
@@ -153,44 +162,109 @@ class ShardedInstance:
         return cls(IJ, K, R, lo, hi, obs, lik, mode, local_eval, align)
 
     def flat_size(self) -> int:
-        return self.R * self.IJ + self.R * self.K + 1
+        """Elements of the contract-form exchange buffer [gS | gC | nll] (the NLL travels as two fp32 words,
+        high and low part of the fp64 partial sum, so that the fp32 all-reduce loses nothing of it)."""
+        return self.R * self.IJ + self.R * self.K + 2
 
-    def evaluate(self, S, C, gather_gS: bool = True):
+    def exchange_bytes(self) -> int:
+        return 4 * (self.flat_size() if self.mode == "flat" else self.R * self.K + 2)
+
+    # ---- one evaluation: local kernel into the persistent buffer, one collective ---------------------------
+    def _local_into(self, buf, Sl, C, off_gs):
+        """Run the local evaluation with its outputs inside ``buf`` where the kernel can write there directly
+        (tcgen05 dense kernel: gS rows with the buffer's row stride, gC in place); otherwise copy."""
+        R, K, IJ, n = self.R, self.K, self.IJ, self.hi - self.lo
+        gC_view = buf[off_gs: off_gs + R * K].view(R, K)
+        tail = buf[off_gs + R * K: off_gs + R * K + 2]
+        direct = False
+        if self.local_eval is _cuda_local_eval:
+            from .dense import DenseObs, nll_fwd_bwd_dense
+            if isinstance(self.obs, DenseObs):
+                gS_view = (buf[: R * IJ].view(R, IJ)[:, self.lo:self.hi] if self.mode == "flat" else
+                           buf[: R * n].view(R, n))
+                nll_fwd_bwd_dense(Sl, C, self.obs, self.lik, out=(self._nll64, gS_view, gC_view))
+                direct = True
+        if not direct:
+            nll, gSl, gC = self.local_eval(Sl.unsqueeze(0), C.reshape(1, R, K), self.obs, self.lik, True)
+            if self.mode == "flat":
+                buf[: R * IJ].view(R, IJ)[:, self.lo:self.hi].copy_(gSl.reshape(R, -1))
+            else:
+                buf[: R * n].view(R, n).copy_(gSl.reshape(R, -1))
+            gC_view.copy_(gC.reshape(R, K))
+            self._nll64.copy_(nll.reshape(1).to(torch.float64))
+        hi32 = self._nll64.to(torch.float32)
+        tail[0:1].copy_(hi32)
+        tail[1:2].copy_((self._nll64 - hi32.to(torch.float64)).to(torch.float32))
+
+    def _step(self, Sl, C):
+        rank, world = _world()
+        R, K, IJ, n = self.R, self.K, self.IJ, self.hi - self.lo
+        buf = self._buf
+        if self.mode == "flat":
+            buf.zero_()                      # the other ranks' pixel blocks must not carry the previous sum
+            self._local_into(buf, Sl, C, R * IJ)
+            if world > 1:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        else:
+            self._local_into(buf, Sl, C, R * n)
+            if world > 1:
+                dist.all_reduce(buf[R * n:], op=dist.ReduceOp.SUM)
+
+    def evaluate(self, S, C, gather_gS: bool = True, cuda_graph: bool = False):
         """``S [R, IJ]`` (full, replicated) or ``[R, hi-lo]`` (this rank's block), ``C [R, K]``
         replicated.  Returns (nll 0-dim fp64, gS, gC [R, K]) where gS is ``[R, IJ]`` (complete on
-        every rank) in "flat" mode or with ``gather_gS``; otherwise this rank's ``[R, hi-lo]``."""
+        every rank) in "flat" mode or with ``gather_gS``; otherwise this rank's ``[R, hi-lo]``.  The returned
+        tensors are views of a persistent buffer that the next call overwrites.  ``cuda_graph``: capture the
+        local kernel and the collective once and replay them (the inputs are copied into staging buffers; pass
+        ``inst._S_in`` / ``inst._C_in`` themselves to skip the copy).  All ranks must make the same sequence of
+        calls with the same ``cuda_graph`` flags."""
         rank, world = _world()
-        R, K, IJ = self.R, self.K, self.IJ
+        R, K, IJ, n = self.R, self.K, self.IJ, self.hi - self.lo
         S2 = S.reshape(R, -1)
         Sl = S2[:, self.lo:self.hi] if S2.shape[1] == IJ else S2
-        if Sl.shape[1] != self.hi - self.lo:
+        if Sl.shape[1] != n:
             raise ValueError("S has neither the full nor the local pixel extent")
-        nll, gSl, gC = self.local_eval(Sl.contiguous().unsqueeze(0), C.reshape(1, R, K).contiguous(), self.obs,
-                                       self.lik, True)
-        gSl, gC, nll = gSl.reshape(R, -1), gC.reshape(R, K), nll.reshape(())
+        Sl = Sl.contiguous()
+        C = C.reshape(R, K).contiguous()
+        dev = C.device
+        size = self.flat_size() if self.mode == "flat" else R * n + R * K + 2
+        if self._buf is None or self._buf.device != dev or self._buf.numel() != size:
+            self._buf = torch.zeros(size, dtype=torch.float32, device=dev)
+            self._nll64 = torch.zeros(1, dtype=torch.float64, device=dev)
+            self._graph = None
+        if cuda_graph and dev.type == "cuda":
+            # The graph is captured ONCE per instance, on staging buffers the instance owns: whether a rank
+            # re-captures must not depend on where its allocator happened to put the caller's tensors (a rank that
+            # re-captures issues one collective more than a rank that replays: deadlock).
+            if self._graph is None:
+                self._S_in, self._C_in = Sl.clone(), C.clone()
+                self._step(self._S_in, self._C_in)   # warm-up outside capture (lazy initialisation of kernels and NCCL)
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step(self._S_in, self._C_in)
+                self._graph = g
+            if Sl.data_ptr() != self._S_in.data_ptr():
+                self._S_in.copy_(Sl)
+            if C.data_ptr() != self._C_in.data_ptr():
+                self._C_in.copy_(C)
+            self._graph.replay()
+        else:
+            self._step(Sl, C)
+        buf = self._buf
+        off = R * IJ if self.mode == "flat" else R * n
+        gC_all = buf[off: off + R * K].view(R, K)
+        nll = buf[off + R * K].to(torch.float64) + buf[off + R * K + 1].to(torch.float64)
         if self.mode == "flat":
-            # the contract form: one fp32 all-reduce of [gS | gC | nll]
-            flat = torch.zeros(self.flat_size(), dtype=torch.float32, device=gC.device)
-            flat[: R * IJ].view(R, IJ)[:, self.lo:self.hi] = gSl
-            flat[R * IJ: R * IJ + R * K] = gC.reshape(-1)
-            flat[-1] = nll.to(torch.float32)
-            if world > 1:
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            return (flat[-1].to(torch.float64), flat[: R * IJ].view(R, IJ), flat[R * IJ: R * IJ + R * K].view(R, K))
-        # pixel-block form: only gC and nll are partial sums (nll kept in fp64)
-        small = torch.empty(R * K + 1, dtype=torch.float64, device=gC.device)
-        small[: R * K] = gC.reshape(-1).to(torch.float64)
-        small[-1] = nll
-        if world > 1:
-            dist.all_reduce(small, op=dist.ReduceOp.SUM)
-        gC_all = small[: R * K].to(torch.float32).view(R, K)
+            return nll, buf[: R * IJ].view(R, IJ), gC_all
+        gSl = buf[: R * n].view(R, n)
         if not gather_gS or world == 1:
-            return small[-1], gSl, gC_all       # (with one rank the local block is the whole map)
+            return nll, gSl, gC_all         # (with one rank the local block is the whole map)
         blocks = [partition_pixels(IJ, world, r, self.align) for r in range(world)]
         width = max(h - l for l, h in blocks)
-        pad = torch.zeros(R, width, dtype=torch.float32, device=gC.device)
-        pad[:, : gSl.shape[1]] = gSl
+        pad = torch.zeros(R, width, dtype=torch.float32, device=dev)
+        pad[:, :n] = gSl
         parts = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(parts, pad)
         gS_all = torch.cat([p[:, : h - l] for p, (l, h) in zip(parts, blocks)], dim=1)
-        return small[-1], gS_all, gC_all
+        return nll, gS_all, gC_all

@@ -288,6 +288,8 @@ CONFIGS = {
     "cfg1": dict(I=51, J=51, K=64, R=4, f=0.10, levels=2, log_domain=False),
     # 3-bit / 8 levels (9 boundaries), log domain (quantization_model_log.py semantics)
     "cfg2": dict(I=101, J=101, K=128, R=8, f=0.20, levels=8, log_domain=True),
+    # one large, densely sampled instance (the tcgen05 path; sharded by pixel blocks over several GPUs)
+    "cfg4": dict(I=512, J=512, K=256, R=16, f=0.50, levels=8, log_domain=True),
 }
 
 
