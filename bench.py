@@ -421,6 +421,29 @@ def cfg4_record(args, rank, world, dev, barrier, reduce_max):
     return rec
 
 
+def bind_to_gpu_numa_node(dev):
+    """Pin this process (and with it the pages of the pinned host buffers it allocates next: first touch) to the NUMA
+    node the GPU hangs off, so that the end-to-end copies do not cross the socket interconnect.  Best effort."""
+    import torch
+    try:
+        p = torch.cuda.get_device_properties(dev)
+        name = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{name}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args, rank: int, world: int, local_rank: int):
     import ctypes as C
 
@@ -429,6 +452,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -541,6 +565,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         d2h = gSh.numel() * 4 + gCh.numel() * 4 + nllh.numel() * 8
         e2e = {"value": nobs_all * args.steps / te.item(), "unit": "observed-entries/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * te.item() / args.steps,
+               "h2d_GBps_per_rank": h2d * args.steps / dt / 1e9, "d2h_GBps_per_rank": d2h * args.steps / dt / 1e9,
+               "host_binding": numa,
                "api": "qmc_nll_fwd_bwd_gather_host (C ABI, pinned host S/C in, nll/gS/gC out; observation set resident)"}
         assert torch.isfinite(nllh).all()
 

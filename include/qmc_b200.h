@@ -6,8 +6,10 @@
  * Every function returns 0 on success and a QMC_ERR_* code otherwise; qmc_last_error() gives the
  * message for the calling thread.  All `*_dev` pointers are device pointers on the current CUDA
  * device, `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  The library
- * never allocates device memory and keeps no global mutable state apart from the thread-local error
- * string: the caller owns every buffer.  There is no CPU implementation behind these entry points.
+ * never allocates device memory: the caller owns every buffer.  Its process-wide state is the thread-local error
+ * string, the launch counter, and -- for qmc_nll_fwd_bwd_gather_host only -- one lazily created set of internal
+ * copy/compute streams per device, guarded by a per-device mutex (calls on one device are serialised, different
+ * devices proceed independently).  There is no CPU implementation behind these entry points.
  *
  * The reference is a Python module namespace, not an FFI; each entry point
  * names the reference function(s) (file:line under /root/reference) whose arithmetic it replaces.
@@ -65,11 +67,10 @@ enum {
                                   contributes (x - (bounds[l] + bounds[l+1])/2)^2, the de-quantised mid-point of
                                   get_quantized_obs_from_ordinal (quantization_model_log.py:43-51) under the cost
                                   norm(Wx*(T_hat - Obs))**2 of qmc_dowjons.ipynb c1:112,130.  noise_std is not
-                                  used; nll_out receives the cost.  Observed-entry kernels only. */
+                                  used; nll_out receives the cost. */
   QMC_EPI_LOGISTIC = 1u << 6   /* logistic instead of Gaussian noise: P = F((hi - x)/s) - F((lo - x)/s) with
                                   F = F_sigmoid (quantization_model.py:43-47) and s = noise_std (s = 1 is the
-                                  reference's F_sigmoid as it stands), evaluated as a stable log-difference.
-                                  Observed-entry kernels only. */
+                                  reference's F_sigmoid as it stands), evaluated as a stable log-difference. */
 };
 
 /*
@@ -123,6 +124,10 @@ typedef struct qmc_obs_view {
   int32_t word_bits;             /* 16 or 32 */
   int32_t lvl_bits;              /* word_bits == 16: width of the level field */
   int32_t has_cont;              /* != 0: continuation rows are in use (bands split over lanes) */
+  int32_t map_modulo;            /* > 0, lane-stream layout with QMC_FORWARD_ONLY: map b of the launch uses the
+                                    observation streams and the C of map b % map_modulo -- D candidate factors S per map
+                                    (the random-restart latent search, qmc.ipynb c1:168-197) are scored in ONE launch of
+                                    B = D * map_modulo maps against one resident observation set */
 } qmc_obs_view_t;
 
 QMC_API int qmc_abi_version(void);
@@ -256,6 +261,13 @@ QMC_API int qmc_get_tensor(const float* S_dev, const float* C_dev, int B, int IJ
  * quantization_model_log.py:104-111) without materialising X_hat.  out_dev: 2*B doubles. */
 QMC_API int qmc_nmse_terms(const float* S_dev, const float* C_dev, const float* X_ref_dev, int B, int IJ,
                    int K, int R, int log_domain, float offset, double* out_dev, void* stream);
+
+/* a9, the one-bit BCE form of the likelihood: NegLikelihood.forward, quantization_model.py:97-113 --
+ * nn.BCELoss()(F_probit(T - mean, std) or F_sigmoid(T - mean), target): mean over the n elements, logarithms
+ * clamped at -100, in the reference's own fp32 arithmetic.  loss_out_dev: one double; gx_out_dev (may be NULL):
+ * d loss / d x as torch's BCELoss backward forms it. */
+QMC_API int qmc_bce_one_bit(const float* x_dev, const float* target_dev, int64_t n, float mean, float noise_std,
+                    int probit, double* loss_out_dev, float* gx_out_dev, void* stream);
 
 /* ---- solver step: what the notebook does with torch.optim.Adam around the path ---- */
 

@@ -35,7 +35,7 @@ class ObsView(C.Structure):
                 ("n_sub", C.c_int32), ("sub_pixels", C.c_int32),
                 ("words_dev", C.c_void_p), ("stream_off_dev", C.c_void_p), ("nrows_dev", C.c_void_p),
                 ("stream_stride", C.c_int64), ("n_runs", C.c_int32), ("word_bits", C.c_int32),
-                ("lvl_bits", C.c_int32), ("has_cont", C.c_int32)]
+                ("lvl_bits", C.c_int32), ("has_cont", C.c_int32), ("map_modulo", C.c_int32)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -68,6 +68,7 @@ SIGNATURES = {
     "qmc_dense_smem_bytes": (_L, [_I, _I]),
     "qmc_get_tensor": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "qmc_nmse_terms": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
+    "qmc_bce_one_bit": (_I, [_P, _P, _L, _F, _F, _I, _P, _P, _P]),
 }
 
 

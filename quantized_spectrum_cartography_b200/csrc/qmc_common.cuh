@@ -163,18 +163,33 @@ __device__ __forceinline__ BinEval probit_one_sided_fast(float thr, float m, flo
 //   P = F(zu) - F(zl) = (1 - e^{-(zu-zl)}) * F(zu) * F(-zl)
 //   log P = log(-expm1(-(zu-zl))) - softplus(-zu) - softplus(zl)       (no cancellation, no overflow)
 //   d(-log P)/dx = (F(-zu) - F(zl)) / s                                (the first term does not depend on x)
-__device__ __forceinline__ float softplus_f(float t) { return fmaxf(t, 0.0f) + log1pf(expf(-fabsf(t))); }
-__device__ __forceinline__ float sigmoid_f(float t) {
-  const float e = expf(-fabsf(t));
-  const float r = 1.0f / (1.0f + e);
-  return t >= 0.0f ? r : e * r;
-}
+// SFU grade, like the probit epilogues: e^{-|t|} is one ex2 and is shared by softplus(t) = max(t, 0) + log1p(e^{-|t|})
+// and F(t) = (t >= 0 ? 1 : e^{-|t|}) / (1 + e^{-|t|}); log1p(e) = ln2 * lg2(1 + e) (absolute error < 2^-23, the
+// terms are O(1)); 3 ex2 + 3 lg2 + 2 rcp per bin.
 __device__ __forceinline__ BinEval logistic_bin(float lo, float hi, float x, float inv_s) {
   const float zl = (lo - x) * inv_s, zu = (hi - x) * inv_s;
   const float width = (hi - lo) * inv_s;  // = zu - zl without the rounding of the two differences
+  const float eu = ex2_approx(-kLog2e * fabsf(zu)), el = ex2_approx(-kLog2e * fabsf(zl));
+  const float ru = rcp_approx(1.0f + eu), rl = rcp_approx(1.0f + el);
+  const float sp_u = fmaxf(-zu, 0.0f) + kLn2 * lg2_approx(1.0f + eu);   // softplus(-zu)
+  const float sp_l = fmaxf(zl, 0.0f) + kLn2 * lg2_approx(1.0f + el);    // softplus(zl)
+  const float f_u = zu <= 0.0f ? ru : eu * ru;                           // F(-zu)
+  const float f_l = zl >= 0.0f ? rl : el * rl;                           // F(zl)
   BinEval o;
-  o.logp = logf(-expm1f(-width)) - softplus_f(-zu) - softplus_f(zl);
-  o.gx = (sigmoid_f(-zu) - sigmoid_f(zl)) * inv_s;
+  o.logp = kLn2 * lg2_approx(1.0f - ex2_approx(-kLog2e * width)) - sp_u - sp_l;
+  o.gx = (f_u - f_l) * inv_s;
+  return o;
+}
+// One-sided logistic bin (the one-bit model with the reference's +-1e5 sentinels): P = F(v), v = (x - thr) * m with
+// m = +1/s for the upper level and -1/s for the lower one; log P = -softplus(-v), d(-log P)/dx = -F(-v) * m.
+// 1 ex2 + 1 lg2 + 1 rcp.
+__device__ __forceinline__ BinEval logistic_one_sided_fast(float thr, float m, float x) {
+  const float v = (x - thr) * m;
+  const float e = ex2_approx(-kLog2e * fabsf(v));
+  const float r = rcp_approx(1.0f + e);
+  BinEval o;
+  o.logp = -(fmaxf(-v, 0.0f) + kLn2 * lg2_approx(1.0f + e));
+  o.gx = -(v <= 0.0f ? r : e * r) * m;
   return o;
 }
 

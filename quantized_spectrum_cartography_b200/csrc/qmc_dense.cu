@@ -39,12 +39,12 @@ struct DenseParams {
   int64_t gs_stride;
   float* gC;             // [R][K]
   int IJ, K, R, Rp8, n_tiles;
-  int n_bounds;
+  int n_bounds, one_sided;
   float inv_a, offset, thr;
   float bounds[QMC_MAX_BOUNDS];
 };
 
-enum : int { DEPI_STABLE = 0, DEPI_REFERENCE = 1, DEPI_ONEBIT = 2 };
+enum : int { DEPI_STABLE = 0, DEPI_REFERENCE = 1, DEPI_ONEBIT = 2, DEPI_LSQ = 3, DEPI_LOGISTIC = 4 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,8 +124,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 // TF32 split: hi keeps the 10 explicit mantissa bits the tensor core reads, lo is the exact rest
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
+// bnd: the boundary table in shared memory (per-lane levels: a shared-memory gather instead of a divergent
+// constant-bank index)
 template <int EPI, bool LOGD>
-__device__ __forceinline__ BinEval dense_eval(const DenseParams& prm, float t, int lvl, float& dxdt) {
+__device__ __forceinline__ BinEval dense_eval(const DenseParams& prm, const float* bnd, float t, int lvl, float& dxdt) {
   float x = t;
   dxdt = 1.0f;
   if (LOGD) {
@@ -133,9 +135,22 @@ __device__ __forceinline__ BinEval dense_eval(const DenseParams& prm, float t, i
     x = logf(u);
     dxdt = 1.0f / u;
   }
+  if (EPI == DEPI_LSQ) {
+    // masked least squares on the bin mid-point (quantization_model_log.py:43-51, qmc_dowjons.ipynb c1:112):
+    // "logp" = -(x - mid)^2, so that nll -= logp accumulates the squared residual
+    const float d = x - 0.5f * (bnd[lvl] + bnd[lvl + 1]);
+    BinEval o;
+    o.logp = -d * d;
+    o.gx = 2.0f * d;
+    return o;
+  }
+  if (EPI == DEPI_LOGISTIC) {  // F_sigmoid in place of F_probit (quantization_model.py:43-47)
+    if (prm.one_sided) return logistic_one_sided_fast(prm.thr, lvl ? prm.inv_a : -prm.inv_a, x);
+    return logistic_bin(bnd[lvl], bnd[lvl + 1], x, prm.inv_a);
+  }
   if (EPI == DEPI_ONEBIT) return probit_one_sided_fast(prm.thr, lvl ? -prm.inv_a : prm.inv_a, x);
-  if (EPI == DEPI_REFERENCE) return probit_bin_reference(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
-  return probit_bin_stable<true>(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
+  if (EPI == DEPI_REFERENCE) return probit_bin_reference(bnd[lvl], bnd[lvl + 1], x, prm.inv_a);
+  return probit_bin_stable<true>(bnd[lvl], bnd[lvl + 1], x, prm.inv_a);
 }
 
 // Shared memory map (bytes).  All operand regions are 128-byte aligned.
@@ -147,9 +162,10 @@ __device__ __forceinline__ BinEval dense_eval(const DenseParams& prm, float t, i
 //   GTh/GTl : g block transposed [chunk of 4 pixels][band][16 B], chunk pitch 528 B (32 rows + 16 B of
 //             padding so that the scalar stores of 32 consecutive pixels hit 32 different banks), plus
 //             512 B of slack because the M = 64 instruction reads 64 rows per chunk
+//   queue   : per warp 32 x DT_SLAB (value, code) pairs: the observed entries of a warp's slab, compacted
 constexpr uint32_t GT_PITCH = 528;
 struct DenseSmem {
-  uint32_t a1, b1, b2h, b2l, b3h, b3l, gh, gl, gth, gtl, total;
+  uint32_t a1, b1, b2h, b2l, b3h, b3l, gh, gl, gth, gtl, queue, total;
 };
 __host__ __device__ inline DenseSmem dense_smem_map(int K, int Rp8) {
   const uint32_t chunks = 3 * Rp8 / 4;
@@ -165,6 +181,7 @@ __host__ __device__ inline DenseSmem dense_smem_map(int K, int Rp8) {
   m.gl = o; o += 8 * 2048;
   m.gth = o; o += 32 * GT_PITCH + 512;
   m.gtl = o; o += 32 * GT_PITCH + 512;
+  m.queue = o; o += (DT_THREADS / 32) * (32 * DT_SLAB) * 8;   // per warp: 32 lanes x DT_SLAB (value, code) pairs
   m.total = o;
   return m;
 }
@@ -175,6 +192,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
   __shared__ uint64_t bar1, bar2;
   __shared__ uint32_t tmem_base_sh;
   __shared__ double wsum[DT_THREADS / 32];
+  __shared__ float bnd[QMC_MAX_BOUNDS + 1];
 
   const int K = prm.K, R = prm.R, Rp8 = prm.Rp8;
   const int chunks1 = 3 * Rp8 / 4;
@@ -194,6 +212,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
     dmbar_init(&bar2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = tid; i < prm.n_bounds; i += DT_THREADS) bnd[i] = prm.bounds[i];
   // B1 (C split for MMA1) and B2h/B2l (C for MMA2): built once, C is the same for every tile
   for (int k = tid; k < K; k += DT_THREADS) {
     float ch[16], cl[16];
@@ -298,20 +317,45 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
       } else {
         cw[0] = cw[1] = 0xffffffffu;
       }
-      // likelihood of the slab: x[] is overwritten by g = dNLL/dt (0 where nothing was observed)
+      // Likelihood of the slab: x[] is overwritten by g = dNLL/dt (0 where nothing was observed).  Only part of
+      // the entries is observed (half at cfg4), so the warp first compacts its observed (value, code) pairs into a
+      // queue in shared memory and then evaluates 32 of them per round with all lanes busy, instead of walking its
+      // DT_SLAB columns with the unobserved lanes idle; the results go back through the queue.
+      {
+        int cnt = 0;
 #pragma unroll
-      for (int c4 = 0; c4 < DT_SLAB / 4; ++c4) {
+        for (int i = 0; i < DT_SLAB; ++i) cnt += ((cw[i >> 2] >> (8 * (i & 3))) & 0xffu) != 255u;
+        int incl = cnt;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int code = (cw[c4] >> (8 * i)) & 0xff;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int base = incl - cnt;
+        uint2* q = reinterpret_cast<uint2*>(dsm + map.queue) + warp * (32 * DT_SLAB);
+        int w = base;
+#pragma unroll
+        for (int i = 0; i < DT_SLAB; ++i) {
+          const uint32_t code = (cw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+          if (code != 255u) q[w++] = make_uint2(__float_as_uint(x[i]), code);
+        }
+        __syncwarp();
+        for (int id = lane; id < total; id += 32) {
+          const uint2 e = q[id];
+          float dxdt;
+          const BinEval ev = dense_eval<EPI, LOGD>(prm, bnd, __uint_as_float(e.x), (int)e.y, dxdt);
+          nll_part -= ev.logp;
+          q[id].x = __float_as_uint(ev.gx * dxdt);
+        }
+        __syncwarp();
+        w = base;
+#pragma unroll
+        for (int i = 0; i < DT_SLAB; ++i) {
+          const uint32_t code = (cw[i >> 2] >> (8 * (i & 3))) & 0xffu;
           float g = 0.0f;
-          if (code != 255) {
-            float dxdt;
-            const BinEval ev = dense_eval<EPI, LOGD>(prm, x[4 * c4 + i], code, dxdt);
-            nll_part -= ev.logp;
-            g = ev.gx * dxdt;
-          }
-          x[4 * c4 + i] = g;
+          if (code != 255u) g = __uint_as_float(q[w++].x);
+          x[i] = g;
         }
       }
       if (GRAD) {
@@ -495,11 +539,7 @@ extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, con
     return set_error(QMC_ERR_UNSUPPORTED, "dense path needs K a multiple of %d and <= 256 (got %d)", DT_BLK, K);
   if (R > DT_RP) return set_error(QMC_ERR_UNSUPPORTED, "dense path needs rank <= %d (got %d)", DT_RP, R);
   QMC_REQUIRE(lik->n_bounds >= 2 && lik->n_bounds <= QMC_MAX_BOUNDS - 1, "n_bounds %d out of range (255 is the 'unobserved' code)", lik->n_bounds);
-  QMC_REQUIRE(lik->noise_std > 0.0f, "noise_std must be positive");
-  if (lik->flags & QMC_EPI_LOGISTIC)
-    return set_error(QMC_ERR_UNSUPPORTED, "QMC_EPI_LOGISTIC: the logistic model runs on the observed-entry kernels only");
-  if (lik->flags & QMC_EPI_LSQ)
-    return set_error(QMC_ERR_UNSUPPORTED, "QMC_EPI_LSQ: the least-squares baseline runs on the observed-entry kernels only");
+  QMC_REQUIRE(lik->noise_std > 0.0f || (lik->flags & QMC_EPI_LSQ), "noise_std must be positive");
   const bool grad = !(lik->flags & QMC_FORWARD_ONLY);
   QMC_REQUIRE(!grad || (gS_out_dev && gC_out_dev), "gradient outputs are NULL without QMC_FORWARD_ONLY");
   cudaStream_t st = (cudaStream_t)stream;
@@ -510,12 +550,22 @@ extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, con
   prm.IJ = IJ; prm.K = K; prm.R = R; prm.Rp8 = R <= 8 ? 8 : 16;
   prm.n_tiles = (IJ + DT_PIX - 1) / DT_PIX;
   prm.n_bounds = lik->n_bounds;
-  prm.inv_a = 1.0f / probit_scale(lik->noise_std);
+  prm.inv_a = (lik->flags & QMC_EPI_LSQ) ? 1.0f                              // least squares has no noise model
+              : (lik->flags & QMC_EPI_LOGISTIC) ? 1.0f / lik->noise_std      // logistic scale, no sqrt(2)
+                                                : 1.0f / probit_scale(lik->noise_std);
+  prm.one_sided = 0;
   prm.offset = lik->offset;
   for (int i = 0; i < lik->n_bounds; ++i) prm.bounds[i] = lik->bounds[i];
   prm.thr = lik->n_bounds >= 3 ? lik->bounds[1] : 0.0f;
   int epi = DEPI_STABLE;
-  if (lik->flags & QMC_EPI_REFERENCE) epi = DEPI_REFERENCE;
+  if (lik->flags & QMC_EPI_LSQ) epi = DEPI_LSQ;
+  else if (lik->flags & QMC_EPI_LOGISTIC) {
+    epi = DEPI_LOGISTIC;
+    if (lik->n_bounds == 3) {
+      const float lo = lik->bounds[0], hi = lik->bounds[2];
+      prm.one_sided = lo <= -1e4f && hi >= 1e4f && (-lo * 0.5f) * prm.inv_a > 110.0f && (hi * 0.5f) * prm.inv_a > 110.0f;
+    }
+  } else if (lik->flags & QMC_EPI_REFERENCE) epi = DEPI_REFERENCE;
   else if (lik->n_bounds == 3) {
     const float lo = lik->bounds[0], hi = lik->bounds[2];
     if (lo <= -1e4f && hi >= 1e4f && (-lo * 0.5f) * prm.inv_a > 30.0f && (hi * 0.5f) * prm.inv_a > 30.0f) epi = DEPI_ONEBIT;
@@ -532,6 +582,8 @@ extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, con
   switch (epi) {
     case DEPI_ONEBIT: return dense_launch<DEPI_ONEBIT>(prm, logd, grad, grid, smem, st);
     case DEPI_REFERENCE: return dense_launch<DEPI_REFERENCE>(prm, logd, grad, grid, smem, st);
+    case DEPI_LSQ: return dense_launch<DEPI_LSQ>(prm, logd, grad, grid, smem, st);
+    case DEPI_LOGISTIC: return dense_launch<DEPI_LOGISTIC>(prm, logd, grad, grid, smem, st);
     default: return dense_launch<DEPI_STABLE>(prm, logd, grad, grid, smem, st);
   }
 }

@@ -77,6 +77,12 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
   prm.word16 = lanes && obs->word_bits == 16;
   prm.lvl_bits = lanes ? obs->lvl_bits : 0;
   prm.has_cont = lanes ? obs->has_cont : 0;
+  prm.map_mod = 0;
+  if (obs->map_modulo > 0) {
+    QMC_REQUIRE(lanes && !grad, "map_modulo (maps sharing one observation set) needs a lane-stream observation set and QMC_FORWARD_ONLY");
+    QMC_REQUIRE(B % obs->map_modulo == 0, "B = %d is not a multiple of map_modulo = %d", B, obs->map_modulo);
+    prm.map_mod = obs->map_modulo;
+  }
   prm.lookahead = 0;
   prm.want_gs = want_gs; prm.want_gc = want_gc;
   prm.fuse_update = fu != nullptr;
@@ -119,6 +125,12 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
     const bool inf_lo = lo < 0 && (-lo * 0.5f) * prm.inv_a > 30.0f;
     const bool inf_hi = hi > 0 && (hi * 0.5f) * prm.inv_a > 30.0f;
     if (inf_lo && inf_hi && fabsf(lo) >= 1e4f && fabsf(hi) >= 1e4f) epi = EPI_ONEBIT;
+  }
+  prm.one_sided = 0;
+  if (epi == EPI_LOGISTIC && lik->n_bounds == 3) {
+    // e^{-|z|} == 0 in fp32 (ex2 flushes) for |z| > 104: the sentinel must sit that far out for any |x| < half its size
+    const float lo = lik->bounds[0], hi = lik->bounds[2];
+    prm.one_sided = lo <= -1e4f && hi >= 1e4f && (-lo * 0.5f) * prm.inv_a > 110.0f && (hi * 0.5f) * prm.inv_a > 110.0f;
   }
   const bool logd = (lik->flags & QMC_LOG_DOMAIN) != 0;
 

@@ -23,6 +23,7 @@ struct GatherParams {
   int word16;                 // lane-stream layout: 16-bit words (two groups per 16 bytes) instead of 32-bit ones
   int lvl_bits;               // 16-bit words: bits of the level field
   int has_cont;               // lane-stream layout: some band is split over several lanes (continuation rows in use)
+  int map_mod;                // lanes kernel, forward only: map b uses the observations and C of map b % map_mod (0 = off)
   int lookahead;              // lanes kernel: CTAs resident on the device (prefetch distance in CTAs)
   int want_gs, want_gc;       // lanes kernel: which gradients the caller needs (QMC_SKIP_GS / QMC_SKIP_GC)
   // fused S-step (qmc_solver_s_step_fused): S is updated in place from the gS tile in shared memory
@@ -45,6 +46,7 @@ struct GatherParams {
   int tiles_per_map, tile_warps;
   float inv_a, offset;
   float thr;  // one-bit fast path threshold
+  int one_sided;  // logistic model: three boundaries whose outer two are numerically infinite
   float bounds[QMC_MAX_BOUNDS];
 };
 
@@ -72,6 +74,7 @@ __device__ __forceinline__ BinEval eval_entry(const GatherParams& prm, float t, 
     o.gx = 2.0f * d;
     return o;
   } else if (EPI == EPI_LOGISTIC) {
+    if (prm.one_sided) return logistic_one_sided_fast(prm.thr, lvl ? prm.inv_a : -prm.inv_a, x);  // uniform branch
     return logistic_bin(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
   } else if (EPI == EPI_ONEBIT) {
     return probit_one_sided_fast(prm.thr, lvl ? -prm.inv_a : prm.inv_a, x);

@@ -125,8 +125,10 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   const int np = min(TP, prm.IJ - p0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nthr = blockDim.x;
+  // candidate batches (random-restart latent search): several maps of the launch share one observation set and C
+  const int bo = prm.map_mod > 0 ? b % prm.map_mod : b;
   const float* __restrict__ Sb = prm.S + b * prm.sB;
-  const float* __restrict__ Cb = prm.C + (int64_t)b * prm.R * K;
+  const float* __restrict__ Cb = prm.C + (int64_t)bo * prm.R * K;
   constexpr bool do_gs = GMODE == 1 || GMODE == 3 || GMODE == 4, do_gc = GMODE == 1 || GMODE == 2;
   constexpr bool FUSE = GMODE == 4;  // bulk layout guaranteed by the host
   float* gSb = (do_gs && !FUSE) ? prm.gS + b * prm.sB : nullptr;
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   if (threadIdx.x == 0) done = 0;
   // every global load of the prologue is issued before anything waits on one of them (the warp issues in
   // order: a store of loaded data would hold back the loads behind it for a full memory round trip)
-  const int64_t stream = (int64_t)b * prm.n_sub + (int64_t)tile * W + warp;
+  const int64_t stream = (int64_t)bo * prm.n_sub + (int64_t)tile * W + warp;
   const uint32_t* sbase = prm.words + (prm.stream_stride > 0 ? stream * prm.stream_stride : prm.stream_off[stream]);
   const uint4* gp = reinterpret_cast<const uint4*>(sbase + (size_t)prm.n_runs * 32) + lane;
   // the run table of the stream (n_runs entries per lane) and SLOTS ring slots of look-ahead, filled by
@@ -197,11 +199,12 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   if (prm.stream_stride > 0 && prm.lookahead > 0 && (int64_t)blockIdx.x + prm.lookahead < (int64_t)gridDim.x) {
     const int nb = blockIdx.x + prm.lookahead;
     const int b2 = nb / prm.tiles_per_map, tile2 = nb - b2 * prm.tiles_per_map;
-    const int64_t stream2 = (int64_t)b2 * prm.n_sub + (int64_t)tile2 * W + warp;
+    const int b2o = prm.map_mod > 0 ? b2 % prm.map_mod : b2;
+    const int64_t stream2 = (int64_t)b2o * prm.n_sub + (int64_t)tile2 * W + warp;
     if (lane < 16) prefetch_l2(reinterpret_cast<const char*>(prm.words + stream2 * prm.stream_stride) + lane * 128);
     if (lane == 16) prefetch_l2(prm.nrows + stream2);
     if (warp == 0 && lane >= 24) {
-      const char* c2 = reinterpret_cast<const char*>(prm.C + (int64_t)b2 * prm.R * K);
+      const char* c2 = reinterpret_cast<const char*>(prm.C + (int64_t)b2o * prm.R * K);
       for (int o = (lane - 24) * 128; o < prm.R * K * 4; o += 8 * 128) prefetch_l2(c2 + o);
     }
     const int np2 = min(TP, prm.IJ - tile2 * TP);

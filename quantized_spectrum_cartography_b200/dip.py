@@ -74,30 +74,55 @@ def _frob(x):
     return torch.linalg.vector_norm(x.reshape(x.shape[0], -1), dim=1)
 
 
-def latent_search(generator, Z, C, nll_fn, cfg: DipConfig, gen: Optional[torch.Generator] = None):
-    """Random-restart latent search (c1:167-196), vectorised over the B maps: draw candidates, keep
-    per map the one with the lowest NLL, then refine around it.  Forward-only evaluations.
+def latent_search(generator, Z, C, nll_fn, cfg: DipConfig, gen: Optional[torch.Generator] = None, candidates_fn=None,
+                  max_images: int = 1 << 17):
+    """Random-restart latent search (c1:167-196), vectorised over the B maps and over the draws: a phase of
+    ``search_draws`` fresh latents, then a phase of ``search_refine`` perturbations (scale ``refine_scale``) of the
+    incumbent of that phase; per map the candidate with the lowest NLL replaces the incumbent if it beats it (the
+    earliest draw wins ties).  Forward-only evaluations.
 
-    (The notebook's refinement loop evaluates the *previous* generator output instead of the
-    perturbed latent -- c1:187-188 reuses ``temp_out`` -- so it can never improve; here the
-    perturbed latent is evaluated, which is what the comment above that loop says it does.)"""
+    ``candidates_fn(S [D*B, R, IJ], C [B, R, K]) -> [D, B]`` scores all D draws of a phase with ONE batched generator
+    forward and ONE likelihood launch (``fused.nll_candidates`` on a lane-stream observation set: the observation
+    streams are shared by reference, not copied); phases whose D*B*R images exceed ``max_images`` are cut into the
+    fewest equal chunks.  Without it the draws are scored one by one through ``nll_fn`` -- the same candidates in the
+    same order, hence the same result (tests/test_gpu_parity.py).
+
+    (The notebook's refinement loop evaluates the *previous* generator output instead of the perturbed latent --
+    c1:187-188 reuses ``temp_out`` -- so it can never improve; here the perturbed latents are evaluated, which is
+    what the comment above that loop says it does.  Refinement draws perturb the incumbent the phase started
+    with, which is what makes them independent of each other and batchable.)"""
     B, R, zd = Z.shape
     with torch.no_grad():
-        best = nll_fn(generator(Z.reshape(B * R, zd)).reshape(B, R, -1), C)
+        best = nll_fn(generator(Z.reshape(B * R, zd)).reshape(B, R, -1), C).to(torch.float64)
         for phase, n in (("draw", cfg.search_draws), ("refine", cfg.search_refine)):
-            for _ in range(n):
-                noise = torch.randn(Z.shape, device=Z.device, generator=gen)
-                cand = noise if phase == "draw" else Z + cfg.refine_scale * noise
-                val = nll_fn(generator(cand.reshape(B * R, zd)).reshape(B, R, -1), C)
-                better = val < best
-                Z[better] = cand[better]
-                best = torch.where(better, val, best)
+            if n <= 0:
+                continue
+            noise = torch.randn((n,) + tuple(Z.shape), device=Z.device, generator=gen)      # [D, B, R, zd]
+            cand = noise if phase == "draw" else Z.unsqueeze(0) + cfg.refine_scale * noise
+            if candidates_fn is None:
+                vals = torch.stack([nll_fn(generator(cand[d].reshape(B * R, zd)).reshape(B, R, -1), C).to(torch.float64)
+                                    for d in range(n)])
+            else:
+                chunks = max(1, -(-(n * B * R) // max_images))
+                per = -(-n // chunks)
+                parts = []
+                for d0 in range(0, n, per):
+                    dc = min(per, n - d0)
+                    parts.append(candidates_fn(generator(cand[d0: d0 + dc].reshape(dc * B * R, zd)).reshape(dc * B, R, -1), C))
+                vals = torch.cat(parts)
+            vmin, dmin = vals.min(dim=0)                                                       # first minimum per map
+            better = vmin < best
+            pick = cand[dmin, torch.arange(B, device=Z.device)]                                 # [B, R, zd]
+            Z[better] = pick[better]
+            best = torch.where(better, vmin, best)
     return Z, best
 
 
 def solve_deep_prior(generator: nn.Module, Z0: torch.Tensor, C0: torch.Tensor, nll_fn: Callable,
-                     cfg: DipConfig = DipConfig(), nmse_fn: Optional[Callable] = None, track_every: int = 0):
-    """``Z0 [B, R, z_dim]``, ``C0 [B, R, K]``; ``nll_fn(S [B,R,IJ], C) -> [B]``."""
+                     cfg: DipConfig = DipConfig(), nmse_fn: Optional[Callable] = None, track_every: int = 0,
+                     candidates_fn: Optional[Callable] = None):
+    """``Z0 [B, R, z_dim]``, ``C0 [B, R, K]``; ``nll_fn(S [B,R,IJ], C) -> [B]``; ``candidates_fn``: the batched
+    scorer of the latent search (:func:`latent_search`)."""
     B, R, zd = Z0.shape
     Z = Z0.detach().clone().requires_grad_(True)
     Cf = C0.detach().clone().requires_grad_(True)
@@ -123,7 +148,7 @@ def solve_deep_prior(generator: nn.Module, Z0: torch.Tensor, C0: torch.Tensor, n
             Cf.clamp_(min=0)
         if it == cfg.search_at:
             with torch.no_grad():
-                latent_search(generator, Z.data, Cf.detach(), nll_fn, cfg)
+                latent_search(generator, Z.data, Cf.detach(), nll_fn, cfg, candidates_fn=candidates_fn)
         opt_z.zero_grad(set_to_none=True)
         S = slf(Z)
         cost = nll_fn(S, Cf.detach()).to(torch.float32) + cfg.lam_c * _frob(Cf.detach()) + cfg.lam_s * _frob(Z)

@@ -90,6 +90,32 @@ def _pixel_major(S3: torch.Tensor) -> bool:
     return S3.stride(1) == 1 and S3.stride(2) == R and (B == 1 or S3.stride(0) == R * IJ)
 
 
+def nll_candidates(S3: torch.Tensor, C3: torch.Tensor, obs: ObsSet, lik: Likelihood) -> torch.Tensor:
+    """Forward-only NLL of D candidate factors per map in ONE launch: ``S3 [D*B, R, IJ]`` (candidate-major: rows
+    d*B .. d*B+B-1 are candidate d of maps 0..B-1), ``C3 [B, R, K]`` shared by a map's candidates, ``obs`` the
+    lane-stream observation set of the B maps (read D times, never copied).  Returns ``[D, B]`` fp64.  The batched
+    random-restart latent search (qmc.ipynb c1:168-197)."""
+    if not obs.lanes:
+        raise ValueError("nll_candidates needs a lane-stream observation set")
+    DB, R, IJ = S3.shape
+    B, K = obs.B, C3.shape[2]
+    if DB % B or C3.shape[:2] != (B, R) or (obs.K, obs.IJ) != (K, IJ):
+        raise ValueError("shapes: S3 [D*B, R, IJ], C3 [B, R, K] for an observation set of B maps")
+    if obs.max_level + 2 > lik.n_bounds:
+        raise ValueError(f"Y contains level {obs.max_level} but the table has only {lik.n_bounds - 1} levels")
+    if not (S3.is_contiguous() or _pixel_major(S3)):
+        S3 = S3.contiguous()
+    C3 = C3.contiguous()
+    lik = _with_flags(lik, True)
+    with torch.cuda.device(S3.device):
+        nll = torch.empty(DB, dtype=torch.float64, device=S3.device)
+        view = obs.view(map_modulo=B)
+        check(lib.qmc_nll_fwd_bwd_gather(S3.data_ptr(), S3.stride(0), S3.stride(1), S3.stride(2), C3.data_ptr(), C.byref(view),
+                                         C.byref(lik), DB, IJ, K, R, _lib.QMC_ALGO_LANES, obs.tile_warps, nll.data_ptr(),
+                                         None, None, _stream()))
+    return nll.reshape(DB // B, B)
+
+
 def nll_fwd_bwd(S3: torch.Tensor, C3: torch.Tensor, obs: ObsSet, lik: Likelihood, *, algo: int = _lib.QMC_ALGO_AUTO,
                 want_grad: bool = True, out=None, skip_gs: bool = False, skip_gc: bool = False):
     """Raw call: S3 [B,R,IJ] fp32 CUDA (emitter-major contiguous, or pixel-major storage viewed
@@ -245,17 +271,30 @@ def make_obs(Y, Wx, K: Optional[int] = None, device=None, *, B: int = 1, R: Opti
     if K is None:
         K = Y.shape[0] if B == 1 else Y.shape[1]
     IJ = Y.numel() // (B * K)
+    lanes_arg = lanes
     if tiled is None:
         tiled = B >= 64 and R is not None
     if tiled:
         if R is None:
             raise ValueError("tiled layout needs R")
+        max_level = int(Y.max().item())                         # decides the width of the stream words
         if lanes is None:
-            lanes = 32 <= K <= 256          # every lane of the warp owns at least one band
-        max_level = int(Y.max().item()) if lanes else None      # decides the width of the stream words
-        n_sub, sub, tw = plan_tiles(IJ, K, R, tile_warps, lanes=lanes, max_level=max_level)
+            # every lane of the warp owns at least one band; level 255 is the lane streams' padding code: a
+            # 256-level table (qmc/utils.py:24) goes through the tiled layout instead
+            lanes = 32 <= K <= 256 and max_level <= 254
+        n_sub, sub, tw = plan_tiles(IJ, K, R, tile_warps, lanes=lanes, max_level=max_level if lanes else None)
         bm = 0 if lanes else bank_mod_for_rank(R)
     else:
         n_sub, sub, tw, bm, lanes = 1, IJ, 0, 0, False
-    return build_obs(Y.to(dev), None if Wx is None else Wx.to(dev), K, IJ, B, n_sub=n_sub, sub_pixels=sub,
-                     tile_warps=tw, bank_mod=bm, lanes=bool(lanes))
+    auto_lanes = lanes_arg is None
+    try:
+        return build_obs(Y.to(dev), None if Wx is None else Wx.to(dev), K, IJ, B, n_sub=n_sub, sub_pixels=sub,
+                         tile_warps=tw, bank_mod=bm, lanes=bool(lanes))
+    except _lib.QmcError as e:
+        # a stream too large for the lane-stream builder's shared memory (huge sub-tiles of a densely sampled
+        # instance): the default selection falls back to the tiled layout, an explicit lanes=True fails loudly
+        if not (lanes and auto_lanes and "builder's shared memory" in str(e)):
+            raise
+        n_sub, sub, tw = plan_tiles(IJ, K, R, tile_warps, lanes=False)
+        return build_obs(Y.to(dev), None if Wx is None else Wx.to(dev), K, IJ, B, n_sub=n_sub, sub_pixels=sub,
+                         tile_warps=tw, bank_mod=bank_mod_for_rank(R), lanes=False)

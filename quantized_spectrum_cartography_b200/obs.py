@@ -99,14 +99,14 @@ class ObsSet:
     def lanes(self) -> bool:
         return self.words is not None
 
-    def view(self) -> ObsView:
+    def view(self, map_modulo: int = 0) -> ObsView:
         return ObsView(self.idx.data_ptr(), self.lvl.data_ptr(), self.row_off.data_ptr(),
                        self.n_sub, self.sub_pixels,
                        self.words.data_ptr() if self.lanes else None,
                        self.stream_off.data_ptr() if self.lanes else None,
                        self.nrows.data_ptr() if self.lanes else None,
                        self.stream_stride if self.lanes else 0,
-                       self.n_runs, self.word_bits, self.lvl_bits, self.has_cont)
+                       self.n_runs, self.word_bits, self.lvl_bits, self.has_cont, map_modulo)
 
     def padding_fraction(self) -> float:
         """Lane-stream layout: fraction of the walked slots that are padding."""
@@ -188,6 +188,10 @@ def build_obs(Y: torch.Tensor, Wx: torch.Tensor | None, K: int, IJ: int, B: int 
     Yc = Y.contiguous().reshape(-1)
     if Yc.numel() != B * K * IJ:
         raise ValueError(f"Y has {Yc.numel()} elements, expected B*K*IJ = {B * K * IJ}")
+    if Y.dtype == torch.int64 and Yc.numel():
+        lo, hi = int(Yc.min().item()), int(Yc.max().item())
+        if lo < 0 or hi > 255:        # the compact format stores one byte per level: do not wrap silently
+            raise ValueError(f"Y holds levels in [{lo}, {hi}]; the compact observation format supports 0..255")
     Wc = None
     if Wx is not None:
         Wc = Wx.to(device=dev, dtype=torch.float32).contiguous().reshape(-1)

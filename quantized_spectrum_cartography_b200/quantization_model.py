@@ -188,21 +188,47 @@ def nmse_factors(S, C_, T_target, offset=None):
     return r[0] if B == 1 else r
 
 
+class _BceOneBit(torch.autograd.Function):
+    """One launch: the BCE value and d loss / d T_sample (qmc_bce_one_bit)."""
+
+    @staticmethod
+    def forward(ctx, Ts, Tt, mean, std, probit):
+        x = Ts.detach().to(torch.float32).contiguous()
+        t = Tt.detach().to(torch.float32).contiguous()
+        if x.numel() != t.numel():
+            raise ValueError("T_sample and T_target differ in size")
+        loss = torch.empty(1, dtype=torch.float64, device=x.device)
+        gx = torch.empty_like(x) if Ts.requires_grad else None
+        with torch.cuda.device(x.device):
+            check(lib.qmc_bce_one_bit(x.data_ptr(), t.data_ptr(), x.numel(), float(mean), 0.0 if std is None else float(std),
+                                      int(bool(probit)), loss.data_ptr(), None if gx is None else gx.data_ptr(), _stream()))
+        if gx is not None:
+            ctx.save_for_backward(gx)
+        ctx.shape = Ts.shape
+        return loss[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (gx,) = ctx.saved_tensors
+        return gx.reshape(ctx.shape) * grad_out, None, None, None, None
+
+
 class NegLikelihood(nn.Module):
     """One-bit BCE form (quantization_model.py:97-113): BCELoss(F_probit(T-mean, std) or
-    F_sigmoid(T-mean), target), mean reduction, no mask, log clamped at -100."""
+    F_sigmoid(T-mean), target), mean reduction, no mask, log clamped at -100 -- one fused CUDA launch for the
+    value and the gradient with respect to T_sample."""
 
     def __init__(self, mean, std=None, probit=True):
         super().__init__()
         if probit:
             assert std is not None
         self.mean, self.std, self.probit = mean, std, probit
-        self.criterion = nn.BCELoss()
 
     def forward(self, T_sample, T_target):
         Ts, Tt = _to_dev(T_sample), _to_dev(T_target)
-        p = F_probit(Ts - self.mean, self.std) if self.probit else F_sigmoid(Ts - self.mean)
-        return self.criterion(p, Tt).to(T_sample.device)
+        mean = float(self.mean.item()) if isinstance(self.mean, torch.Tensor) else float(self.mean)
+        std = None if self.std is None else (float(self.std.item()) if isinstance(self.std, torch.Tensor) else float(self.std))
+        return _BceOneBit.apply(Ts, Tt, mean, std, self.probit).to(T_sample.device)
 
 
 class DeterministicCost(nn.Module):

@@ -159,6 +159,90 @@ def test_fused_nll_and_gradients_vs_reference(tag, q, nll_golden, fixture_instan
             assert rel_err(C.grad.numpy(), c["gC"].numpy()) < GRAD_RTOL
 
 
+@pytest.mark.parametrize("algo", ["tiled", "lanes", "lanes_pixel_major", "dense"])
+@pytest.mark.parametrize("tag", all_case_tags())
+def test_golden_cases_through_every_kernel(tag, algo, q, nll_golden, fixture_instance):
+    """The reference-minted golden vectors (qmc/onebitdata1.mat, 9 models x 4 evaluation points) through the
+    kernels the drop-in call does not pick for a single small instance: the tiled and the lane-stream observed-entry
+    kernels (the headline kernel; emitter-major and pixel-major S) and the tcgen05 dense kernel.  Against the
+    reference itself where it is accurate, against the float64 oracle everywhere."""
+    from quantized_spectrum_cartography_b200 import _lib, dense
+    c = nll_case_inputs(nll_golden, fixture_instance, tag)
+    R, K = c["C"].shape
+    IJ = c["S"].numel() // R
+    lik = q.make_likelihood(c["bb"], c["sigma"], offset=c["offset"])
+    S3 = c["S"].reshape(1, R, IJ).cuda()
+    C3 = c["C"].reshape(1, R, K).cuda()
+    Y, Wx = c["Y"].cuda(), c["Wx"].cuda()
+    before = q._lib.launch_count()
+    if algo == "dense":
+        dobs = dense.pack_dense(Y, Wx, K)
+        nll, gS, gC = dense.nll_fwd_bwd_dense(S3[0], C3[0], dobs, lik)
+        nll, gS, gC = nll.reshape(1), gS.unsqueeze(0), gC.unsqueeze(0)
+    else:
+        lanes = algo.startswith("lanes")
+        n_sub, sub, tw = q.plan_tiles(IJ, K, R, 8, lanes=lanes, max_level=int(Y.max().item()))
+        obs = q.build_obs(Y, Wx, K, IJ, 1, n_sub=n_sub, sub_pixels=sub, tile_warps=tw,
+                          bank_mod=0 if lanes else q.bank_mod_for_rank(R), lanes=lanes)
+        if algo == "lanes_pixel_major":
+            S3 = S3.transpose(1, 2).contiguous().transpose(1, 2)
+        nll, gS, gC = q.nll_fwd_bwd(S3, C3, obs, lik, algo=_lib.QMC_ALGO_LANES if lanes else _lib.QMC_ALGO_TILED)
+    assert q._lib.launch_count() > before
+    nll64, gS64, gC64, pmin = oc.nll_and_grads_fp64(c["S"], c["C"], c["Y"], c["Wx"], c["bb"], c["sigma"],
+                                                    offset=c["offset"], sentinels=c["sentinels"])
+    assert nll[0].item() == pytest.approx(nll64, rel=NLL_RTOL)
+    gS_h, gC_h = gS[0].contiguous().cpu().numpy(), gC[0].cpu().numpy()
+    if np.linalg.norm(gS64) > 0:
+        assert rel_err(gS_h, gS64.reshape(R, -1)) < GRAD_RTOL
+        assert rel_err(gC_h, gC64) < GRAD_RTOL
+    else:
+        assert np.abs(gS_h).max() == 0 and np.abs(gC_h).max() == 0
+    if not np.isnan(c["nll"]) and c["Pmin_all"] >= 1e-5:          # the reference itself, where it is accurate
+        assert nll[0].item() == pytest.approx(c["nll"], rel=NLL_RTOL)
+        if c["gS"].abs().max() > 0:
+            assert rel_err(gS_h, c["gS"].reshape(R, -1).numpy()) < GRAD_RTOL
+            assert rel_err(gC_h, c["gC"].numpy()) < GRAD_RTOL
+
+
+def test_256_level_table_falls_back_to_the_tiled_layout(q):
+    """The reference's 256-level table (QUANTIZATION_BOUNDARIES_256_BINS_UNIFORM, qmc/utils.py:24) uses level 255, the
+    lane streams' padding code: the default layout selection must fall back to the tiled layout (not raise), an
+    explicit lanes=True must fail loudly, and out-of-range labels are refused instead of wrapped into a byte."""
+    t = load_golden("tables.npz")
+    bb = torch.from_numpy(t["QUANTIZATION_BOUNDARIES_256_BINS_UNIFORM"])
+    assert bb.numel() == 257
+    B, I, J, K, R = 64, 9, 8, 32, 4
+    g = torch.Generator().manual_seed(3)
+    S = torch.rand(B, R, I * J, generator=g) * 0.3 + 0.05
+    C = torch.rand(B, R, K, generator=g) * 0.4 + 0.1
+    T = torch.einsum("brp,brk->bkp", S, C)
+    T = T / T.max() * float(bb[-2])
+    sigma = float(bb[2] - bb[1]) * 2
+    Y = oc.assign_levels(T + sigma * torch.randn(T.shape, generator=g), bb)
+    Y[0, 0, 0] = 255                                            # make sure the top level is in use
+    Wx = torch.bernoulli(torch.full(T.shape, 0.5), generator=g)
+    Wx[0, 0, 0] = 1
+    obs = q.make_obs(Y.cuda(), Wx.cuda(), K, "cuda", B=B, R=R)   # default selection: tiled, not lanes
+    assert not obs.lanes and obs.max_level == 255 and obs.tile_warps > 0
+    lik = q.make_likelihood(bb, sigma, sentinels=False)
+    nll, gS, gC = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik)
+    for b in (0, B - 1):
+        want = oc.nll_and_grads_fp64(S[b].reshape(R, 1, I, J), C[b], Y[b].reshape(K, 1, I, J), Wx[b].reshape(K, 1, I, J),
+                                     bb, sigma, sentinels=False)
+        assert nll[b].item() == pytest.approx(want[0], rel=NLL_RTOL)
+        assert rel_err(gS[b].cpu().numpy(), want[1].reshape(R, -1)) < GRAD_RTOL
+        assert rel_err(gC[b].cpu().numpy(), want[2]) < GRAD_RTOL
+    with pytest.raises(ValueError, match="254"):
+        q.make_obs(Y.cuda(), Wx.cuda(), K, "cuda", B=B, R=R, lanes=True)
+    Ybad = Y.clone()
+    Ybad[1, 2, 3] = 256
+    with pytest.raises(ValueError, match="0..255"):
+        q.make_obs(Ybad.cuda(), Wx.cuda(), K, "cuda", B=B, R=R)
+    Ybad[1, 2, 3] = -1
+    with pytest.raises(ValueError, match="0..255"):
+        q.build_obs(Ybad.cuda(), Wx.cuda(), K, I * J, B)
+
+
 def test_reference_epilogue_loses_the_tails_like_the_reference(q, nll_golden, fixture_instance):
     """QMC_EPI_REFERENCE evaluates P literally like the reference, 0.5*(1+erf(zu)) - 0.5*(1+erf(zl))
     in fp32.  At sigma = 1e-4 / zero start min P is 5 * 2^-24: P is quantised to multiples of 2^-24,
@@ -305,6 +389,20 @@ def test_thin_compositional_surface(q, fixture_instance):
     target = (T_true > 5e-4).float()
     assert qm.NegLikelihood(5e-4, std=0.008)(T_s, target).item() == pytest.approx(float(m["bce_probit"]), rel=1e-5)
     assert qm.NegLikelihood(5e-4, probit=False)(T_s, target).item() == pytest.approx(float(m["bce_sigmoid"]), rel=1e-5)
+    # the tails, where the reference's fp32 p saturates and BCELoss clamps the logarithm at -100
+    assert qm.NegLikelihood(5e-4, std=1e-4)(T_s, target).item() == pytest.approx(float(m["bce_probit_tail"]), rel=1e-4)
+    # one fused launch (qmc_bce_one_bit) whose gradient is what autograd gives the reference's composition
+    before = q._lib.launch_count()
+    for probit, std in ((True, 0.008), (False, None)):
+        Tg = T_s.clone().cuda().requires_grad_(True)
+        loss = qm.NegLikelihood(5e-4, std=std, probit=probit)(Tg, target.cuda())
+        loss.backward()
+        Tr = T_s.clone().requires_grad_(True)
+        want = oc.neg_likelihood_bce(Tr, target, 5e-4, std, probit=probit)
+        want.backward()
+        assert loss.item() == pytest.approx(want.item(), rel=1e-5)
+        assert rel_err(Tg.grad.cpu().numpy(), Tr.grad.numpy()) < GRAD_RTOL
+    assert q._lib.launch_count() == before + 2
     np.testing.assert_allclose(qm.F_sigmoid(torch.from_numpy(m["F_sigmoid_x"])).numpy(), m["F_sigmoid_y"], rtol=2e-6)
     np.testing.assert_allclose(qm.F_probit(torch.from_numpy(m["F_probit_x"]), 0.008).numpy(), m["F_probit_y"], rtol=2e-6, atol=2e-7)
     bb7 = torch.from_numpy(t["QUANTIZATION_BOUNDARIES_7_ADJUSTED"])
@@ -551,6 +649,100 @@ def test_deep_prior_step_matches_oracle_loop(q):
     assert torch.all(best <= before + 1e-9)
 
 
+def test_latent_search_in_one_launch_per_phase(q):
+    """the random-restart latent search (qmc.ipynb c1:168-197) scores all draws of a phase with one
+    batched generator forward and ONE likelihood launch -- D*B maps against the B maps' resident lane streams, shared
+    by reference (qmc_obs_view_t.map_modulo) -- and picks exactly what the draw-by-draw search picks."""
+    from quantized_spectrum_cartography_b200 import _lib, dip, qmc
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, R, K, I, J = 5, 4, 64, 51, 51
+    torch.manual_seed(1)
+    gen = dip.Generator256().eval().cuda()
+    Z0 = torch.randn(B, R, 256, device="cuda")
+    C0 = (torch.rand(B, R, K) * 0.2 + 0.05).cuda()
+    with torch.no_grad():
+        S_true = gen(torch.randn(B * R, 256, device="cuda")).reshape(B, R, -1)
+    T = torch.einsum("brp,brk->bkp", S_true, C0)
+    thr = T.median().item()
+    bb = torch.tensor([0.0, thr, 10.0])
+    sigma = 0.25 * thr
+    Y = (T + sigma * torch.randn(T.shape, device="cuda") > thr).to(torch.uint8)
+    Wx = torch.bernoulli(torch.full(T.shape, 0.1, device="cuda"))
+    lik = q.make_likelihood(bb, sigma)
+    obs = q.make_obs(Y, Wx, K, "cuda", B=B, R=R, tiled=True, lanes=True)
+    nll_fn = qmc.cuda_nll_fn(obs, lik)
+    cfg = dip.DipConfig(search_draws=24, search_refine=24)
+    # candidate scoring alone: one launch, same numbers as map-by-map evaluations of the same factors
+    D = 7
+    with torch.no_grad():
+        Sc = gen(torch.randn(D * B * R, 256, device="cuda")).reshape(D * B, R, -1)
+    before = _lib.launch_count()
+    vals = q.nll_candidates(Sc, C0, obs, lik)
+    assert _lib.launch_count() == before + 1 and vals.shape == (D, B)
+    for d in range(D):
+        np.testing.assert_allclose(vals[d].cpu().numpy(), q.nll_fwd_bwd(Sc[d * B:(d + 1) * B], C0, obs, lik, want_grad=False)[0].cpu().numpy(),
+                                   rtol=1e-12)
+    # the search: batched == draw by draw (same RNG stream, same candidates, same kernel arithmetic)
+    Za, Zb = Z0.clone(), Z0.clone()
+    ga, gb = torch.Generator(device="cuda").manual_seed(7), torch.Generator(device="cuda").manual_seed(7)
+    _, best_seq = dip.latent_search(gen, Za, C0, nll_fn, cfg, gen=ga)
+    before = _lib.launch_count()
+    _, best_bat = dip.latent_search(gen, Zb, C0, nll_fn, cfg, gen=gb, candidates_fn=lambda S, C: q.nll_candidates(S, C, obs, lik))
+    assert _lib.launch_count() - before <= 4                      # incumbent + one launch per phase
+    assert torch.equal(Za, Zb)
+    # (cuDNN may pick another convolution algorithm for the larger generator batch: the factors agree to fp32 rounding)
+    np.testing.assert_allclose(best_bat.cpu().numpy(), best_seq.cpu().numpy(), rtol=1e-7)
+    with torch.no_grad():
+        start = nll_fn(gen(Z0.reshape(B * R, 256)).reshape(B, R, -1), C0)
+    assert torch.all(best_bat <= start.to(torch.float64) + 1e-9) and torch.any(best_bat < start.to(torch.float64))
+
+
+def test_deep_prior_loop_nmse_on_a_64_map_batch(q):
+    """cfg5 at batch scale: 64 maps x 4 emitters (generator batch 256), the lane-stream kernel as the loss.  The loop
+    driven by the CUDA likelihood and the same loop driven by the float64-checked CPU oracle end at the same NMSE of the
+    recovered tensor within 1e-4 (north star), cuDNN/cuBLAS TF32 disabled."""
+    from quantized_spectrum_cartography_b200 import dip, qmc
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, R, K, I, J = 64, 4, 64, 51, 51
+    torch.manual_seed(2)
+    gen = dip.Generator256().eval()
+    Z0 = torch.randn(B, R, 256)
+    with torch.no_grad():
+        S_true = gen(torch.randn(B * R, 256)).reshape(B, R, -1)
+    C_true = torch.rand(B, R, K) * 0.2 + 0.05
+    C0 = 0.8 * C_true
+    T = torch.einsum("brp,brk->bkp", S_true, C_true)
+    thr = T.median().item()
+    bb = torch.tensor([0.0, thr, 10.0])
+    sigma = 0.25 * thr
+    Y = oc.assign_levels(T + sigma * torch.randn(T.shape), bb)
+    Wx = torch.bernoulli(torch.full(T.shape, 0.1))
+    cfg = dip.DipConfig(iters=3, lam_c=1.0, lam_s=0.1, search_at=-1)
+
+    def oracle_nll(S, C):
+        return torch.stack([oc.masked_nll(S[b].reshape(R, 1, I, J), C[b], Y[b].reshape(K, 1, I, J),
+                                          Wx[b].reshape(K, 1, I, J), bb, sigma, vectorised=True) for b in range(B)])
+
+    def nmse(S, C):
+        X = torch.einsum("brp,brk->bkp", S.cpu().double(), C.cpu().double())
+        Td = T.double()
+        return (torch.linalg.vector_norm((X - Td).reshape(B, -1), dim=1) / torch.linalg.vector_norm(Td.reshape(B, -1), dim=1))
+
+    ref = dip.solve_deep_prior(gen, Z0, C0, oracle_nll, cfg)
+    gen_d = dip.Generator256().eval()
+    gen_d.load_state_dict(gen.state_dict())
+    gen_d.cuda()
+    obs = q.make_obs(Y.cuda(), Wx.cuda(), K, "cuda", B=B, R=R, tiled=True, lanes=True)
+    assert obs.lanes
+    lik = q.make_likelihood(bb, sigma)
+    got = dip.solve_deep_prior(gen_d, Z0.cuda(), C0.cuda(), qmc.cuda_nll_fn(obs, lik), cfg)
+    n_ref, n_got = nmse(ref["S"], ref["C"]), nmse(got["S"], got["C"])
+    assert float((n_got - n_ref).abs().max()) < 1e-4, float((n_got - n_ref).abs().max())
+    assert rel_err(got["C"].cpu().numpy(), ref["C"].numpy()) < 1e-4
+
+
 @pytest.mark.parametrize("IJ,K,R,levels,log_domain,f", [(300, 64, 4, 2, False, 0.5), (1000, 128, 16, 8, False, 0.5),
                                                        (515, 256, 16, 8, True, 0.5), (128, 96, 9, 4, False, 0.9),
                                                        (4096, 256, 16, 2, False, 0.3)])
@@ -771,7 +963,7 @@ def test_least_squares_baseline_vs_reference(name, q, fixture_instance):
 @pytest.mark.parametrize("algo", ["flat", "tiled", "lanes"])
 def test_least_squares_batched_all_kernels(q, R, levels, log_domain, algo):
     """The least-squares epilogue in every observed-entry kernel: per-map cost and gradients equal the
-    float64 oracle's (ragged and empty maps included); the dense path refuses the flag."""
+    float64 oracle's (ragged and empty maps included); the dense tcgen05 kernel agrees."""
     from quantized_spectrum_cartography_b200 import _lib, dense
     B, I, J, K = 4, 17, 13, 32
     S, C, Y, Wx, bb, sigma, off = _random_instance(B, I, J, K, R, 0.3, levels, seed=7 * R + levels, log_domain=log_domain)
@@ -798,10 +990,13 @@ def test_least_squares_batched_all_kernels(q, R, levels, log_domain, algo):
         assert rel_err(gC[b].cpu().numpy(), want[2]) < GRAD_RTOL
     cost_f, _, _ = q.nll_fwd_bwd(S.cuda(), C.cuda(), obs, lik, algo=a, want_grad=False)
     np.testing.assert_allclose(cost_f.cpu().numpy(), cost.cpu().numpy(), rtol=1e-12)
-    if algo == "flat" and R == 4:
+    if algo == "flat":
+        # the same epilogue in the dense tcgen05 kernel
         dobs = dense.pack_dense(Y[0].cuda(), Wx[0].cuda(), K)
-        with pytest.raises(_lib.QmcError, match="least-squares"):
-            dense.nll_fwd_bwd_dense(S[0].cuda(), C[0].cuda(), dobs, lik)
+        dn, dgS, dgC = dense.nll_fwd_bwd_dense(S[0].cuda(), C[0].cuda(), dobs, lik)
+        assert dn.item() == pytest.approx(cost[0].item(), rel=NLL_RTOL)
+        assert rel_err(dgS.cpu().numpy(), gS[0].cpu().numpy()) < GRAD_RTOL
+        assert rel_err(dgC.cpu().numpy(), gC[0].cpu().numpy()) < GRAD_RTOL
 
 
 def test_least_squares_solver_matches_torch_loop(q):
@@ -840,7 +1035,8 @@ def test_least_squares_solver_matches_torch_loop(q):
 @pytest.mark.parametrize("algo", ["flat", "tiled", "lanes"])
 def test_logistic_model_all_kernels(q, R, levels, log_domain, sentinels, algo):
     """QMC_EPI_LOGISTIC in every observed-entry kernel against the tail-stable float64 statement of
-    P = F_sigmoid((U-x)/s) - F_sigmoid((W-x)/s): NLL 1e-5, gradients 1e-4; the dense path refuses the flag."""
+    P = F_sigmoid((U-x)/s) - F_sigmoid((W-x)/s): NLL 1e-5, gradients 1e-4; the dense tcgen05 kernel evaluates the same
+    epilogue (and the least-squares one)."""
     from quantized_spectrum_cartography_b200 import _lib, dense
     B, I, J, K = 4, 17, 13, 32
     S, C, Y, Wx, bb, sigma, off = _random_instance(B, I, J, K, R, 0.3, levels, seed=11 * R + levels, log_domain=log_domain)
@@ -868,11 +1064,22 @@ def test_logistic_model_all_kernels(q, R, levels, log_domain, sentinels, algo):
             continue
         assert rel_err(gS[b].cpu().numpy(), want[1].reshape(R, -1)) < GRAD_RTOL
         assert rel_err(gC[b].cpu().numpy(), want[2]) < GRAD_RTOL
-    if algo == "flat" and R == 4:
-        # the drop-in call and the refusal of the dense kernel
+    if algo == "flat":
+        # the drop-in call
         Sg = S[0].reshape(R, 1, I, J).cuda().requires_grad_(True)
-        v = q.qmc_nll(Sg, C[0].cuda(), Y[0].reshape(K, 1, I, J), Wx[0].reshape(K, 1, I, J), bb, scale, model="logistic")
+        v = q.qmc_nll(Sg, C[0].cuda(), Y[0].reshape(K, 1, I, J), Wx[0].reshape(K, 1, I, J), bb, scale, offset=off,
+                      sentinels=sentinels, model="logistic")
         assert v.item() == pytest.approx(nll[0].item(), rel=1e-6)
-        dobs = dense.pack_dense(Y[0].cuda(), Wx[0].cuda(), K)
-        with pytest.raises(_lib.QmcError, match="logistic"):
-            dense.nll_fwd_bwd_dense(S[0].cuda(), C[0].cuda(), dobs, lik)
+        # the dense tcgen05 kernel with the logistic and the least-squares epilogues (3xTF32 products: fp32-grade)
+        for b in (0, 3):
+            dobs = dense.pack_dense(Y[b].cuda(), Wx[b].cuda(), K)
+            dn, dgS, dgC = dense.nll_fwd_bwd_dense(S[b].cuda(), C[b].cuda(), dobs, lik)
+            assert dn.item() == pytest.approx(nll[b].item(), rel=NLL_RTOL)
+            assert rel_err(dgS.cpu().numpy(), gS[b].cpu().numpy()) < GRAD_RTOL
+            assert rel_err(dgC.cpu().numpy(), gC[b].cpu().numpy()) < GRAD_RTOL
+            lik_lsq = q.make_likelihood(bb, None, offset=off, least_squares=True)
+            ln, lgS, lgC = dense.nll_fwd_bwd_dense(S[b].cuda(), C[b].cuda(), dobs, lik_lsq)
+            want = oc.lsq_and_grads_fp64(S[b].reshape(R, 1, I, J), C[b], Y[b].reshape(K, 1, I, J), Wx[b].reshape(K, 1, I, J), bb, off)
+            assert ln.item() == pytest.approx(want[0], rel=NLL_RTOL)
+            assert rel_err(lgS.cpu().numpy(), want[1].reshape(R, -1)) < GRAD_RTOL
+            assert rel_err(lgC.cpu().numpy(), want[2]) < GRAD_RTOL
