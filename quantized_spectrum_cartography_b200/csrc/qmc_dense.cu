@@ -25,7 +25,8 @@ namespace qmc {
 constexpr int DT_PIX = 128;    // pixels per tile = TMEM lanes
 constexpr int DT_BLK = 32;     // bands per G block
 constexpr int DT_RP = 16;      // padded rank of the gradient MMAs (N)
-constexpr int DT_THREADS = 512;   // 16 warps: 4 per TMEM lane quadrant, each takes an 8-band slab of a block
+constexpr int DT_THREADS = 512;   // 16 epilogue warps: 4 per TMEM lane quadrant, each takes an 8-band slab of a block
+constexpr int DT_LAUNCH = DT_THREADS + 32;   // + one warp that only issues the tensor-core instructions
 constexpr int DT_SLAB = DT_BLK / (DT_THREADS / 128);
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_D2 = 256, COL_D3 = 272;
@@ -187,11 +188,11 @@ __host__ __device__ inline DenseSmem dense_smem_map(int K, int Rp8) {
 }
 
 template <int EPI, bool LOGD, bool GRAD>
-__global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams prm) {
+__global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams prm) {
   extern __shared__ __align__(1024) uint8_t dsm[];
-  __shared__ uint64_t bar1, bar2;
+  __shared__ uint64_t bar1, bar2, gfull;
   __shared__ uint32_t tmem_base_sh;
-  __shared__ double wsum[DT_THREADS / 32];
+  __shared__ double wsum[DT_LAUNCH / 32];
   __shared__ float bnd[QMC_MAX_BOUNDS + 1];
 
   const int K = prm.K, R = prm.R, Rp8 = prm.Rp8;
@@ -199,6 +200,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
   const DenseSmem map = dense_smem_map(K, Rp8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant, which 8-band slab of a 32-band block
+  // Warp specialisation: warps 0..15 evaluate the likelihood and write the G operands; warp 16 issues every
+  // tcgen05.mma.  The epilogue warps hand a block's G over through the `gfull` mbarrier and go straight on to the next
+  // block's arithmetic -- they never wait for each other (no CTA barrier inside a tile) nor for the issue of ~60 MMA
+  // instructions; they only wait (bar2) for the previous block's MMAs before overwriting the G buffers.
+  const bool issuer = warp == DT_THREADS / 32;
   const int row = quad * 32 + lane;              // pixel row of this thread inside the tile
   const uint32_t sbase = s_u32(dsm);
 
@@ -210,6 +216,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
   if (tid == 0) {
     dmbar_init(&bar1, 1);
     dmbar_init(&bar2, 1);
+    dmbar_init(&gfull, DT_THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < prm.n_bounds; i += DT_THREADS) bnd[i] = prm.bounds[i];
@@ -248,12 +255,18 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
 
   float nll_part = 0.0f;   // per tile (<= 256 terms) in fp32, folded into nll_acc in fp64 after every tile
   double nll_acc = 0.0;
-  uint32_t ph1 = 0, ph2 = 0;
+  uint32_t ph1 = 0, ph2 = 0, phg = 0;
   bool d3_started = false;   // D3 blocks accumulate over all tiles of this CTA
   const int nblk = K / DT_BLK;
 
   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
     const int p0 = tile * DT_PIX;
+    // the code bytes of a block are fetched one block ahead (the first block's here, before the tile is staged):
+    // their DRAM latency hides behind the staging, MMA1 and, later, a block's arithmetic
+    const bool inside = p0 + row < prm.IJ;
+    const uint8_t* crow = prm.code + (size_t)(p0 + row) * K;
+    uint2 cnext = make_uint2(0xffffffffu, 0xffffffffu);
+    if (inside && !issuer) cnext = __ldg(reinterpret_cast<const uint2*>(crow + half * DT_SLAB));
     // ---- stage the S tile: A1 (MMA1) and B3h/B3l (MMA3) -------------------------------------------
     if (tid < 256) {
       const int p = tid & 127, rh = tid >> 7;   // pixel, rank half (8 ranks each)
@@ -289,7 +302,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
     tc_fence_before();
     __syncthreads();
     // ---- MMA1: D1 = [Sh|Sh|Sl] * [Ch|Cl|Ch]^T ------------------------------------------------------
-    if (tid == 0) {
+    if (issuer && lane == 0) {
       tc_fence_after();
       const int ksteps = 3 * Rp8 / 8;
       for (int ks = 0; ks < ksteps; ++ks) {
@@ -299,24 +312,50 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
       }
       umma_commit(&bar1);
     }
-    dmbar_wait(&bar1, ph1);
+    if (!issuer) {
+      dmbar_wait(&bar1, ph1);
+      tc_fence_after();
+    }
     ph1 ^= 1;
-    tc_fence_after();
 
     // ---- epilogue, one 64-band block at a time ------------------------------------------------------
-    const bool inside = p0 + row < prm.IJ;
-    const uint8_t* crow = prm.code + (size_t)(p0 + row) * K;
     for (int blk = 0; blk < nblk; ++blk) {
+      if (issuer) {
+        if (GRAD && lane == 0) {
+          dmbar_wait(&gfull, phg);   // all sixteen epilogue warps have written this block's G operands
+          tc_fence_after();
+          // MMA2: D2[128 x 16] += G_blk * C_blk   (K = 32 bands of this block, 4 steps of 8)
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t ga = (term == 2) ? map.gl : map.gh;
+            const uint32_t cb = (term == 1) ? map.b2l : map.b2h;
+            for (int ks = 0; ks < DT_BLK / 8; ++ks) {
+              const uint64_t ad = umma_desc(sbase + ga + ks * 2 * 2048, 2048, 128);
+              const uint64_t bd = umma_desc(sbase + cb + (blk * (DT_BLK / 4) + ks * 2) * 256, 256, 128);
+              umma_tf32(tmem + COL_D2, ad, bd, idesc2, (blk | term | ks) != 0);
+            }
+          }
+          // MMA3: D3_blk[bands x 16] += G_blk^T * S_tile   (K = 128 pixels, 16 steps of 8; M = 64
+          // instruction whose rows 32..63 read the following chunk and are never looked at)
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t ga = (term == 2) ? map.gtl : map.gth;
+            const uint32_t sb = (term == 1) ? map.b3l : map.b3h;
+            for (int ks = 0; ks < DT_PIX / 8; ++ks) {
+              const uint64_t ad = umma_desc(sbase + ga + ks * 2 * GT_PITCH, GT_PITCH, 128);
+              const uint64_t bd = umma_desc(sbase + sb + ks * 2 * 256, 256, 128);
+              umma_tf32(tmem + COL_D3 + blk * DT_RP, ad, bd, idesc3, d3_started || (term | ks) != 0);
+            }
+          }
+          umma_commit(&bar2);
+        }
+        phg ^= 1;
+        continue;
+      }
       const int k0 = blk * DT_BLK + half * DT_SLAB;   // first band of this thread's 8-column slab
       float x[DT_SLAB];
       tmem_ld8(tlane + (uint32_t)k0, x);
       uint32_t cw[DT_SLAB / 4];
-      if (inside) {
-        const uint2 c0 = __ldg(reinterpret_cast<const uint2*>(crow + k0));
-        cw[0] = c0.x; cw[1] = c0.y;
-      } else {
-        cw[0] = cw[1] = 0xffffffffu;
-      }
+      cw[0] = cnext.x; cw[1] = cnext.y;
+      if (inside && blk + 1 < nblk) cnext = __ldg(reinterpret_cast<const uint2*>(crow + k0 + DT_BLK));
       // Likelihood of the slab: x[] is overwritten by g = dNLL/dt (0 where nothing was observed).  Only part of
       // the entries is observed (half at cfg4), so the warp first compacts its observed (value, code) pairs into a
       // queue in shared memory and then evaluates 32 of them per round with all lanes busy, instead of walking its
@@ -341,12 +380,16 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
           if (code != 255u) q[w++] = make_uint2(__float_as_uint(x[i]), code);
         }
         __syncwarp();
-        for (int id = lane; id < total; id += 32) {
-          const uint2 e = q[id];
-          float dxdt;
-          const BinEval ev = dense_eval<EPI, LOGD>(prm, bnd, __uint_as_float(e.x), (int)e.y, dxdt);
-          nll_part -= ev.logp;
-          q[id].x = __float_as_uint(ev.gx * dxdt);
+        for (int id = lane; id < total; id += 64) {   // two entries per lane and pass: independent chains for the scheduler
+          const bool two = id + 32 < total;
+          const uint2 e0 = q[id];
+          const uint2 e1 = two ? q[id + 32] : e0;
+          float d0, d1;
+          const BinEval v0 = dense_eval<EPI, LOGD>(prm, bnd, __uint_as_float(e0.x), (int)e0.y, d0);
+          const BinEval v1 = dense_eval<EPI, LOGD>(prm, bnd, __uint_as_float(e1.x), (int)e1.y, d1);
+          nll_part -= v0.logp + (two ? v1.logp : 0.0f);
+          q[id].x = __float_as_uint(v0.gx * d0);
+          if (two) q[id + 32].x = __float_as_uint(v1.gx * d1);
         }
         __syncwarp();
         w = base;
@@ -382,38 +425,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
           *reinterpret_cast<float*>(dsm + map.gtl + ot + 32) = l4.z;
           *reinterpret_cast<float*>(dsm + map.gtl + ot + 48) = l4.w;
         }
-        fence_async();
+        fence_async();       // generic-proxy writes of G -> visible to the tensor core's async proxy
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-          tc_fence_after();
-          // MMA2: D2[128 x 16] += G_blk * C_blk   (K = 32 bands of this block, 4 steps of 8)
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t ga = (term == 2) ? map.gl : map.gh;
-            const uint32_t cb = (term == 1) ? map.b2l : map.b2h;
-            for (int ks = 0; ks < DT_BLK / 8; ++ks) {
-              const uint64_t ad = umma_desc(sbase + ga + ks * 2 * 2048, 2048, 128);
-              const uint64_t bd = umma_desc(sbase + cb + (blk * (DT_BLK / 4) + ks * 2) * 256, 256, 128);
-              umma_tf32(tmem + COL_D2, ad, bd, idesc2, (blk | term | ks) != 0);
-            }
-          }
-          // MMA3: D3_blk[bands x 16] += G_blk^T * S_tile   (K = 128 pixels, 16 steps of 8; M = 64
-          // instruction whose rows 32..63 read the following chunk and are never looked at)
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t ga = (term == 2) ? map.gtl : map.gth;
-            const uint32_t sb = (term == 1) ? map.b3l : map.b3h;
-            for (int ks = 0; ks < DT_PIX / 8; ++ks) {
-              const uint64_t ad = umma_desc(sbase + ga + ks * 2 * GT_PITCH, GT_PITCH, 128);
-              const uint64_t bd = umma_desc(sbase + sb + ks * 2 * 256, 256, 128);
-              umma_tf32(tmem + COL_D3 + blk * DT_RP, ad, bd, idesc3, d3_started || (term | ks) != 0);
-            }
-          }
-          umma_commit(&bar2);
-        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&gfull)) : "memory");
       }
     }
     d3_started = true;
-    if (GRAD) {
+    if (GRAD && !issuer) {
       // ---- gS tile out of D2 ---------------------------------------------------------------------
       dmbar_wait(&bar2, ph2);
       ph2 ^= 1;
@@ -436,7 +455,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
   }
 
   // ---- gC out of D3, NLL -----------------------------------------------------------------------------
-  if (GRAD && blockIdx.x < prm.n_tiles) {
+  if (GRAD && blockIdx.x < prm.n_tiles && !issuer) {
     tc_fence_after();
     if (half == 0 && quad < 2) {
       for (int blk = 0; blk < nblk; ++blk) {
@@ -459,7 +478,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_kernel(const DenseParams 
   __syncthreads();
   if (tid == 0) {
     double tot = 0.0;
-    for (int i = 0; i < DT_THREADS / 32; ++i) tot += wsum[i];
+    for (int i = 0; i < DT_LAUNCH / 32; ++i) tot += wsum[i];
     if (tot != 0.0) atomicAdd(prm.nll, tot);
   }
   if (warp == 0) {
@@ -496,7 +515,7 @@ static int dense_launch(const DenseParams& prm, bool logd, bool grad, int grid, 
   do {                                                                                                       \
     auto kern = dense_kernel<EPI, L, G>;                                                                     \
     QMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    kern<<<grid, DT_THREADS, smem, st>>>(prm);                                                               \
+    kern<<<grid, DT_LAUNCH, smem, st>>>(prm);                                                               \
   } while (0)
   if (logd) { if (grad) QMC_DENSE_GO(true, true); else QMC_DENSE_GO(true, false); }
   else { if (grad) QMC_DENSE_GO(false, true); else QMC_DENSE_GO(false, false); }
