@@ -132,9 +132,11 @@ __device__ __forceinline__ BinEval dense_eval(const DenseParams& prm, const floa
   float x = t;
   dxdt = 1.0f;
   if (LOGD) {
+    // SFU grade like the rest of the epilogue: lg2.approx is good to 2^-22 absolute in log2 units, far below what the
+    // bin widths (>= 0.1 in log units) can see; a non-positive argument gives NaN / -inf exactly as logf does
     const float u = t + prm.offset;
-    x = logf(u);
-    dxdt = 1.0f / u;
+    x = (EPI == DEPI_REFERENCE) ? logf(u) : kLn2 * lg2_approx(u);
+    dxdt = (EPI == DEPI_REFERENCE) ? 1.0f / u : rcp_approx(u);
   }
   if (EPI == DEPI_LSQ) {
     // masked least squares on the bin mid-point (quantization_model_log.py:43-51, qmc_dowjons.ipynb c1:112):
@@ -381,6 +383,14 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
         }
         __syncwarp();
         for (int id = lane; id < total; id += 64) {   // two entries per lane and pass: independent chains for the scheduler
+          if (id - lane + 32 >= total) {              // (warp-uniform) at most 32 entries left: a single evaluation each
+            const uint2 e0 = q[id];
+            float d0;
+            const BinEval v0 = dense_eval<EPI, LOGD>(prm, bnd, __uint_as_float(e0.x), (int)e0.y, d0);
+            nll_part -= v0.logp;
+            q[id].x = __float_as_uint(v0.gx * d0);
+            break;
+          }
           const bool two = id + 32 < total;
           const uint2 e0 = q[id];
           const uint2 e1 = two ? q[id + 32] : e0;
