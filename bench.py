@@ -488,9 +488,17 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     for _ in range(args.warmup):
         step()
     barrier()
+    # clocks: nvidia-smi needs a few hundred ms to start and samples every 100 ms, the timed region is a few ms.
+    # The sampler therefore starts here and the same step runs back to back for ~0.7 s (an extended warm-up, so that
+    # the samples are taken under exactly the timed load) straight into the timed region.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.7:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     launches0 = _lib.launch_count()
     barrier()

@@ -186,11 +186,11 @@ extern "C" int qmc_nmse_terms(const float* S_dev, const float* C_dev, const floa
 // that the host->device copy of one chunk, the kernel of the previous one and the device->host copy of
 // the one before overlap (PCIe is full duplex; the kernel is a small fraction of either copy).
 namespace {
-constexpr int kPipeStreams = 4;
+constexpr int kPipeStreams = 3;
 struct HostPipe {  // per device: copy/compute streams and the event that orders them after the caller's
   std::mutex mu;   // calls on one device are serialised; different devices proceed independently
   bool ready = false;
-  cudaStream_t s[kPipeStreams] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t s[kPipeStreams] = {nullptr, nullptr, nullptr};
   cudaEvent_t start = nullptr;
 };
 constexpr int kMaxDevices = 64;
@@ -221,8 +221,9 @@ extern "C" int qmc_nll_fwd_bwd_gather_host(const float* S_host, const float* C_h
   for (auto& x : g_pipe.s) QMC_CUDA_CHECK(cudaStreamWaitEvent(x, g_pipe.start, 0));
 
   // enough chunks that the fill and drain of the pipeline (one chunk's copy in, one chunk's copy out) are a small
-  // part of the whole, few enough that a chunk's kernel still fills the device
-  const int n_chunks = B >= 2048 ? 16 : (B >= 512 ? 8 : (B >= 64 ? 4 : 1));
+  // part of the whole, few enough that a chunk's copies stay long (measured on the B200 host: 8 chunks on 3 streams
+  // 4.46 ms per cfg3 step, 16 chunks on 4 streams 4.84 ms)
+  const int n_chunks = B >= 512 ? 8 : (B >= 64 ? 4 : 1);
   const int per = (B + n_chunks - 1) / n_chunks;
   int rc_all = QMC_OK;
   const size_t sS = (size_t)R * IJ, sC = (size_t)R * K;
