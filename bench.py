@@ -113,9 +113,11 @@ class ClockSampler:
 # workload
 # -------------------------------------------------------------------------------------------------
 def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_budget_kb: int = 110, bank_mod: int = -1,
-                   lanes: bool = True):
+                   lanes: bool = True, ctas_per_map: int = 1):
     """cfg3 on one GPU: synthetic maps, one-bit observations, tiled compact observation set.
-    Seeds: `seed` data, `seed+1` noise and mask."""
+    Seeds: `seed` data, `seed+1` noise and mask.  ``ctas_per_map`` > 1 keeps the sub-tiles (one per
+    warp, hence the streams' lengths) and groups them into that many smaller CTAs per map: a finer unit for the
+    block scheduler when a GPU holds only a wave or two of maps."""
     import torch
 
     import quantized_spectrum_cartography_b200 as q
@@ -144,6 +146,8 @@ def build_workload(n_maps: int, device, seed: int, tile_warps: int = 8, smem_bud
     del noisy
     Wx = torch.bernoulli(torch.full(T.shape, c["sampling"], device=device), generator=gen)
     n_sub, sub, tw = q.plan_tiles(IJ, K, R, tile_warps, smem_budget_kb * 1024, lanes=lanes, max_level=c["levels"] - 1)
+    if ctas_per_map > 1 and n_sub == tw and tw % ctas_per_map == 0:
+        tw //= ctas_per_map
     obs = q.build_obs(Y, Wx, K, IJ, n_maps, n_sub=n_sub, sub_pixels=sub, tile_warps=tw,
                       bank_mod=0 if lanes else (bank_mod if bank_mod >= 0 else q.bank_mod_for_rank(R)), lanes=lanes)
     lik = q.make_likelihood(bb, sigma)
@@ -377,8 +381,9 @@ def cfg4_record(args, rank, world, dev, barrier, reduce_max):
     rec = {"shape": f"{I}x{J}x{K}", "rank": R, "sampling": c["f"], "levels": c["levels"], "log_domain": bool(c["log_domain"]),
            "observed_entries": nobs, "kernel": "dense_kernel (tcgen05 kind::tf32, 3xTF32)", "modes": {}}
     n_it = max(args.steps, 10)
-    for mode in (("flat", "pixel_block") if world > 1 else ("pixel_block",)):
-        inst = parallel.ShardedInstance.from_dense(Y, Wx, K, R, lik, mode=mode, align=128, dense=True)
+    for tag in (("flat", "pixel_block", "pixel_block_peer") if world > 1 else ("pixel_block",)):
+        mode, exchange = ("pixel_block", "peer") if tag == "pixel_block_peer" else (tag, "nccl")
+        inst = parallel.ShardedInstance.from_dense(Y, Wx, K, R, lik, mode=mode, align=128, dense=True, exchange=exchange)
         Sl = S[:, inst.lo:inst.hi].contiguous()
         use_graph = True
         try:
@@ -399,11 +404,30 @@ def cfg4_record(args, rank, world, dev, barrier, reduce_max):
         m = {"ms_per_eval": ms, "entries_per_s": nobs / (ms * 1e-3), "exchange_bytes": inst.exchange_bytes() if world > 1 else 0,
              "cuda_graph": use_graph, "pixels_per_gpu": inst.hi - inst.lo}
         off = R * IJ if mode == "flat" else R * (inst.hi - inst.lo)
-        local = lambda: inst._local_into(inst._buf, Sl, Cm_in, off)
-        for _ in range(3):
-            local()
-        m["local_kernel_ms"] = reduce_max(_timed(local, n_it, stream, barrier))
-        if world > 1:
+        if exchange == "peer":
+            m["exchange"] = ("fused into dense_kernel: the last CTA stores [gC | nll] into every peer's region over NVLink "
+                             "(CUDA IPC peer mappings), flags, waits, sums in rank order; no collective call")
+            m["exchange_status"] = inst.exchange_status()
+        else:
+            # the local part alone (kernel + packing of the NLL words), as its own CUDA graph
+            local = lambda: inst._local_into(inst._buf, Sl, Cm_in, off)
+            for _ in range(3):
+                local()
+            torch.cuda.synchronize()
+            gl = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gl):
+                local()
+            for _ in range(3):
+                gl.replay()
+            m["local_kernel_ms"] = reduce_max(_timed(gl.replay, n_it, torch.cuda.current_stream(), barrier))
+            del gl
+        if world > 1 and exchange == "peer":
+            nll, gS, gC = inst.evaluate(Sl, Cm_in, gather_gS=False, cuda_graph=use_graph)
+            gS_ref = ref[1][:, inst.lo:inst.hi]
+            m["err_vs_one_gpu"] = {"nll": abs(nll.item() / ref[0].item() - 1), "gS": float((gS - gS_ref).norm() / gS_ref.norm()),
+                                   "gC": float((gC - ref[2]).norm() / ref[2].norm())}
+            inst.close()
+        elif world > 1:
             coll = (lambda: dist.all_reduce(inst._buf)) if mode == "flat" else (lambda: dist.all_reduce(inst._buf[off:]))
             for _ in range(3):
                 coll()
@@ -412,7 +436,7 @@ def cfg4_record(args, rank, world, dev, barrier, reduce_max):
             gS_ref = ref[1] if mode == "flat" else ref[1][:, inst.lo:inst.hi]
             m["err_vs_one_gpu"] = {"nll": abs(nll.item() / ref[0].item() - 1), "gS": float((gS - gS_ref).norm() / gS_ref.norm()),
                                    "gC": float((gC - ref[2]).norm() / ref[2].norm())}
-        rec["modes"][mode] = m
+        rec["modes"][tag] = m
         del inst
     d = dense.DenseObs(torch.empty(0), IJ, K, nobs, 0)
     best = min(v["ms_per_eval"] for v in rec["modes"].values())

@@ -250,6 +250,38 @@ QMC_API int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, const 
 /* Shared-memory bytes of the dense kernel for a geometry (0 = unsupported). */
 QMC_API int64_t qmc_dense_smem_bytes(int K, int R);
 
+/* ---- sharded instance: factor-gradient exchange fused into the dense kernel (peer memory over NVLink) --------
+ * Replaces, for the pixel-block sharding of one oversized instance (BASELINE configs[3]), the separate collective
+ * that follows the reference's `backward()` when the sum of qmc/qmc.ipynb c1:150 is split over devices: every rank
+ * evaluates its pixel block, and the kernel's last CTA writes the rank's partial [gC | nll] into a slot of every
+ * peer's exchange region (plain stores through NVLink peer mappings), publishes a flag, waits for the peers' flags
+ * and adds the slots up in rank order -- every rank ends with the same bits, no NCCL call, no second launch.
+ *
+ * An exchange region is device memory of qmc_peer_region_bytes() bytes allocated by qmc_peer_alloc (which also
+ * returns the 64-byte CUDA IPC handle the other ranks open with qmc_peer_open; exchange the handles with any host
+ * mechanism, e.g. torch.distributed.all_gather_object).  All ranks must issue the same sequence of exchange calls
+ * on a region set; a peer that never arrives makes the kernel give up after ~2 s and set the region's status word
+ * (qmc_peer_status != 0). */
+#define QMC_PEER_MAX_WORLD 8
+typedef struct qmc_peer_exchange {
+  int32_t rank, world;                 /* 1 <= world <= QMC_PEER_MAX_WORLD */
+  int32_t slot_floats;                 /* capacity of one slot in floats (>= R*K + 2) */
+  int32_t reserved;
+  void* region[QMC_PEER_MAX_WORLD];    /* region[q]: rank q's exchange region as mapped into THIS process */
+} qmc_peer_exchange_t;
+QMC_API int64_t qmc_peer_region_bytes(int world, int slot_floats);
+QMC_API int qmc_peer_alloc(int64_t bytes, void** region_out_dev, void* ipc_handle_out64);
+QMC_API int qmc_peer_open(const void* ipc_handle64, void** region_out_dev);
+QMC_API int qmc_peer_close(void* region_dev);   /* a region opened with qmc_peer_open */
+QMC_API int qmc_peer_free(void* region_dev);    /* a region allocated with qmc_peer_alloc */
+QMC_API int qmc_peer_status(const void* own_region_dev, int* status_out, void* stream);   /* synchronises the stream */
+/* qmc_nll_fwd_bwd_dense on this rank's pixel block + the fused exchange: on return of the kernel nll_out_dev and
+ * gC_out_dev hold the sums over all ranks (gS_out_dev: this rank's block, complete by construction). */
+QMC_API int qmc_nll_fwd_bwd_dense_exchange(const float* S_dev, const float* C_dev, const uint8_t* code_dev,
+                                   const qmc_likelihood_t* lik, int IJ, int K, int R, double* nll_out_dev,
+                                   float* gS_out_dev, int64_t gs_row_stride, float* gC_out_dev,
+                                   const qmc_peer_exchange_t* px, void* stream);
+
 /* ---- a1/a2/a10 helpers kept importable by the reference's call surface ------------------------ */
 
 /* X[b][k][p] = sum_r S[b][r][p]*C[b][r][k] (+ optional log link): get_tensor, quantization_model.py:79-86 */

@@ -38,6 +38,15 @@ class ObsView(C.Structure):
                 ("lvl_bits", C.c_int32), ("has_cont", C.c_int32), ("map_modulo", C.c_int32)]
 
 
+QMC_PEER_MAX_WORLD = 8
+
+
+class PeerExchange(C.Structure):
+    """qmc_peer_exchange_t"""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("slot_floats", C.c_int32), ("reserved", C.c_int32),
+                ("region", C.c_void_p * QMC_PEER_MAX_WORLD)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # every symbol include/qmc_b200.h declares: name -> (restype, argtypes)
@@ -66,6 +75,14 @@ SIGNATURES = {
     "qmc_dense_pack": (_I, [_P, _I, _P, _I, _I, _I, _P, _P]),
     "qmc_nll_fwd_bwd_dense": (_I, [_P, _P, _P, C.POINTER(Likelihood), _I, _I, _I, _P, _P, _L, _P, _P]),
     "qmc_dense_smem_bytes": (_L, [_I, _I]),
+    "qmc_peer_region_bytes": (_L, [_I, _I]),
+    "qmc_peer_alloc": (_I, [_L, C.POINTER(C.c_void_p), _P]),
+    "qmc_peer_open": (_I, [_P, C.POINTER(C.c_void_p)]),
+    "qmc_peer_close": (_I, [_P]),
+    "qmc_peer_free": (_I, [_P]),
+    "qmc_peer_status": (_I, [_P, C.POINTER(C.c_int), _P]),
+    "qmc_nll_fwd_bwd_dense_exchange": (_I, [_P, _P, _P, C.POINTER(Likelihood), _I, _I, _I, _P, _P, _L, _P,
+                                            C.POINTER(PeerExchange), _P]),
     "qmc_get_tensor": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "qmc_nmse_terms": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
     "qmc_bce_one_bit": (_I, [_P, _P, _L, _F, _F, _I, _P, _P, _P]),

@@ -40,10 +40,108 @@ struct DenseParams {
   int64_t gs_stride;
   float* gC;             // [R][K]
   int IJ, K, R, Rp8, n_tiles;
+  int tile_pix;          // pixels a tile really holds (<= DT_PIX; the rest of the 128 TMEM lanes idles), chosen by the host so
+                         // that the tiles divide evenly over the persistent CTAs
   int n_bounds, one_sided;
   float inv_a, offset, thr;
+  // fused factor-gradient exchange of a sharded instance (px_world == 0: none); see peer_exchange()
+  int px_rank, px_world, px_slot_floats;
+  uint8_t* px_region[QMC_PEER_MAX_WORLD];
   float bounds[QMC_MAX_BOUNDS];
 };
+
+// ---- exchange region (one per rank, device memory mapped into every peer through CUDA IPC) -------------------------
+//   [0, 256)  header: epoch (exchanges completed), status (0 = fine, 1 = a peer never arrived), done (CTA counter)
+//             and, from byte 128, flag[q] = the last epoch rank q has delivered into this region
+//   then two sets (epoch parity) of `world` slots of slot_floats floats: slot q = rank q's partial [gC | nll as a double]
+// A rank can run at most one exchange ahead of a peer (it needs the peer's flag of epoch e to finish e, and the peer
+// raises it only after it has read everything of epoch e-1), hence two slot sets and a monotonic flag are enough.
+struct PeerHeader {
+  uint32_t epoch, status, done, pad[29];
+  uint32_t flag[32];
+};
+static_assert(sizeof(PeerHeader) == 256, "PeerHeader is the first 256 bytes of a region");
+__host__ __device__ inline size_t peer_slot_offset(int world, int slot_floats, int parity, int q) {
+  return sizeof(PeerHeader) + ((size_t)parity * world + q) * (size_t)slot_floats * 4;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Run by the last CTA of the grid to finish (every CTA's gC / NLL atomics are complete and visible): push this rank's
+// partial [gC | nll] into slot `rank` of every rank's region with plain stores over NVLink, raise the flags, wait for
+// the peers' flags in the own region and add the slots up in rank order (every rank gets the same bits).
+__device__ void peer_exchange(const DenseParams& prm, int nthreads) {
+  const int tid = threadIdx.x, world = prm.px_world, rank = prm.px_rank;
+  const int n = prm.R * prm.K, n4 = n >> 2;            // K is a multiple of 32: n % 4 == 0
+  PeerHeader* own = reinterpret_cast<PeerHeader*>(prm.px_region[rank]);
+  const uint32_t e = own->epoch + 1;                   // written only by this code path, one kernel at a time
+  const int par = (int)(e & 1u);
+  const float4* part = reinterpret_cast<const float4*>(prm.gC);
+  const double nll_part = __ldcg(prm.nll);
+  for (int q0 = 0; q0 < world; ++q0) {
+    const int q = (rank + 1 + q0) % world;             // start with the neighbour: the ranks do not all hit rank 0 first
+    float4* dst = reinterpret_cast<float4*>(prm.px_region[q] + peer_slot_offset(world, prm.px_slot_floats, par, rank));
+    for (int i = tid; i < n4; i += nthreads) dst[i] = __ldcg(part + i);
+    if (tid == 0) *reinterpret_cast<double*>(dst + n4) = nll_part;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int px_failed;
+  if (tid == 0) px_failed = 0;
+  __syncthreads();
+  if (tid < world) {
+    st_release_sys(&reinterpret_cast<PeerHeader*>(prm.px_region[tid])->flag[rank], e);
+    const uint64_t t0 = globaltimer_ns();
+    // flags are monotonic; the comparison is wrap-safe
+    while ((int32_t)(ld_acquire_sys(&own->flag[tid]) - e) < 0) {
+      if (globaltimer_ns() - t0 > 2000000000ull) { px_failed = 1; break; }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (px_failed) {
+    if (tid == 0) { own->status = 1; own->done = 0; own->epoch = e; }
+    return;
+  }
+  const uint8_t* slots = prm.px_region[rank] + peer_slot_offset(world, prm.px_slot_floats, par, 0);
+  const size_t pitch = (size_t)prm.px_slot_floats * 4;
+  for (int i = tid; i < n4; i += nthreads) {
+    float4 a = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(slots) + i);
+    for (int q = 1; q < world; ++q) {
+      const float4 b = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(slots + q * pitch) + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(prm.gC)[i] = a;
+  }
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int q = 0; q < world; ++q) {
+      const unsigned long long* p = reinterpret_cast<const unsigned long long*>(slots + q * pitch + (size_t)n * 4);
+      unsigned long long bits;
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(bits) : "l"(p) : "memory");
+      tot += __longlong_as_double((long long)bits);
+    }
+    *prm.nll = tot;
+    own->done = 0;
+    own->epoch = e;
+  }
+}
 
 enum : int { DEPI_STABLE = 0, DEPI_REFERENCE = 1, DEPI_ONEBIT = 2, DEPI_LSQ = 3, DEPI_LOGISTIC = 4 };
 
@@ -260,24 +358,29 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
   uint32_t ph1 = 0, ph2 = 0, phg = 0;
   bool d3_started = false;   // D3 blocks accumulate over all tiles of this CTA
   const int nblk = K / DT_BLK;
+  const bool short_tile = prm.tile_pix < DT_PIX;
 
   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
-    const int p0 = tile * DT_PIX;
+    const int p0 = tile * prm.tile_pix;
     // the code bytes of a block are fetched one block ahead (the first block's here, before the tile is staged):
     // their DRAM latency hides behind the staging, MMA1 and, later, a block's arithmetic
-    const bool inside = p0 + row < prm.IJ;
-    const uint8_t* crow = prm.code + (size_t)(p0 + row) * K;
+    // A short tile spreads its pixels evenly over the four TMEM lane quadrants (pixel = 4 * lane + quadrant): every
+    // warp then compacts the same number of observed entries
+    const int pix = short_tile ? ((row & 31) << 2 | (row >> 5)) : row;
+    const bool inside = pix < prm.tile_pix && p0 + pix < prm.IJ;
+    const uint8_t* crow = prm.code + (size_t)(p0 + pix) * K;
     uint2 cnext = make_uint2(0xffffffffu, 0xffffffffu);
     if (inside && !issuer) cnext = __ldg(reinterpret_cast<const uint2*>(crow + half * DT_SLAB));
     // ---- stage the S tile: A1 (MMA1) and B3h/B3l (MMA3) -------------------------------------------
     if (tid < 256) {
-      const int p = tid & 127, rh = tid >> 7;   // pixel, rank half (8 ranks each)
-      const bool inside = p0 + p < prm.IJ;
+      const int p = tid & 127, rh = tid >> 7;   // operand row (= TMEM lane), rank half (8 ranks each)
+      const int ppix = short_tile ? ((p & 31) << 2 | (p >> 5)) : p;
+      const bool inside = ppix < prm.tile_pix && p0 + ppix < prm.IJ;
       float sh[8], sl[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rh * 8 + i;
-        const float s = (inside && r < R) ? __ldg(prm.S + (size_t)r * prm.IJ + p0 + p) : 0.0f;
+        const float s = (inside && r < R) ? __ldg(prm.S + (size_t)r * prm.IJ + p0 + ppix) : 0.0f;
         sh[i] = tf32_hi(s);
         sl[i] = s - sh[i];
         const uint32_t o = (p >> 2) * 256 + (r >> 3) * 128 + (r & 7) * 16 + (p & 3) * 4;
@@ -453,7 +556,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
         if (inside) {
 #pragma unroll
           for (int r = 0; r < 16; ++r)
-            if (r < R) prm.gS[(size_t)r * prm.gs_stride + p0 + row] = v[r];
+            if (r < R) prm.gS[(size_t)r * prm.gs_stride + p0 + pix] = v[r];
         }
       }
     }
@@ -493,6 +596,19 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
   }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+  }
+  if (GRAD && prm.px_world > 0) {
+    // the last CTA to get here owns the exchange (its peers' atomics are ordered before their counter increment)
+    __shared__ int px_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      PeerHeader* own = reinterpret_cast<PeerHeader*>(prm.px_region[prm.px_rank]);
+      px_last = atomicAdd(&own->done, 1u) == gridDim.x - 1;
+      __threadfence();
+    }
+    __syncthreads();
+    if (px_last) peer_exchange(prm, DT_LAUNCH);
   }
 }
 
@@ -558,9 +674,9 @@ extern "C" int64_t qmc_dense_smem_bytes(int K, int R) {
   return (int64_t)dense_smem_map(K, R <= 8 ? 8 : 16).total;
 }
 
-extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, const uint8_t* code_dev,
-                                     const qmc_likelihood_t* lik, int IJ, int K, int R, double* nll_out_dev,
-                                     float* gS_out_dev, int64_t gs_row_stride, float* gC_out_dev, void* stream) {
+static int dense_entry(const float* S_dev, const float* C_dev, const uint8_t* code_dev, const qmc_likelihood_t* lik,
+                       int IJ, int K, int R, double* nll_out_dev, float* gS_out_dev, int64_t gs_row_stride,
+                       float* gC_out_dev, const qmc_peer_exchange_t* px, void* stream) {
   QMC_REQUIRE(S_dev && C_dev && code_dev && lik && nll_out_dev, "null argument");
   QMC_REQUIRE(IJ > 0 && R > 0, "bad sizes");
   QMC_REQUIRE(gs_row_stride == 0 || gs_row_stride >= IJ, "gs_row_stride %lld is smaller than IJ", (long long)gs_row_stride);
@@ -577,7 +693,35 @@ extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, con
   prm.S = S_dev; prm.C = C_dev; prm.code = code_dev; prm.nll = nll_out_dev; prm.gS = gS_out_dev; prm.gC = gC_out_dev;
   prm.gs_stride = gs_row_stride > 0 ? gs_row_stride : IJ;
   prm.IJ = IJ; prm.K = K; prm.R = R; prm.Rp8 = R <= 8 ? 8 : 16;
-  prm.n_tiles = (IJ + DT_PIX - 1) / DT_PIX;
+  prm.px_rank = 0; prm.px_world = 0; prm.px_slot_floats = 0;
+  for (int q = 0; q < QMC_PEER_MAX_WORLD; ++q) prm.px_region[q] = nullptr;
+  if (px) {
+    QMC_REQUIRE(grad, "the fused exchange combines gradients: QMC_FORWARD_ONLY is not supported with it");
+    QMC_REQUIRE(px->world >= 1 && px->world <= QMC_PEER_MAX_WORLD && px->rank >= 0 && px->rank < px->world,
+                "bad rank %d / world %d", px->rank, px->world);
+    QMC_REQUIRE(px->slot_floats >= R * K + 2 && (px->slot_floats % 4) == 0,
+                "slot_floats %d: need a multiple of 4 that is >= R*K + 2 = %d", px->slot_floats, R * K + 2);
+    for (int q = 0; q < px->world; ++q) {
+      QMC_REQUIRE(px->region[q] != nullptr, "region[%d] is NULL", q);
+      prm.px_region[q] = (uint8_t*)px->region[q];
+    }
+    prm.px_rank = px->rank; prm.px_world = px->world; prm.px_slot_floats = px->slot_floats;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  {
+    // The work of a tile is its observed entries (the epilogue compacts them), not its 128 TMEM lanes: size the tiles
+    // so that every persistent CTA gets the same number of them.  256 full tiles on 148 CTAs (cfg4 on one of eight
+    // GPUs) take two rounds of 128 pixels; 296 tiles of 111 pixels take two rounds of 111.
+    const int64_t full = ((int64_t)IJ + DT_PIX - 1) / DT_PIX;
+    const int64_t rounds = (full + sms - 1) / sms;
+    int64_t tp = ((int64_t)IJ + rounds * sms - 1) / (rounds * sms);
+    tp = (tp + 7) & ~(int64_t)7;
+    if (const char* e = getenv("QMC_DENSE_TILE_PIX")) tp = atoi(e);   // measurement hook
+    prm.tile_pix = (int)(tp < 8 ? 8 : tp > DT_PIX ? DT_PIX : tp);
+  }
+  prm.n_tiles = (IJ + prm.tile_pix - 1) / prm.tile_pix;
   prm.n_bounds = lik->n_bounds;
   prm.inv_a = (lik->flags & QMC_EPI_LSQ) ? 1.0f                              // least squares has no noise model
               : (lik->flags & QMC_EPI_LOGISTIC) ? 1.0f / lik->noise_std      // logistic scale, no sqrt(2)
@@ -604,9 +748,6 @@ extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, con
   QMC_CUDA_CHECK(cudaMemsetAsync(nll_out_dev, 0, sizeof(double), st));
   if (grad) QMC_CUDA_CHECK(cudaMemsetAsync(gC_out_dev, 0, sizeof(float) * (size_t)R * K, st));
   const size_t smem = dense_smem_map(K, prm.Rp8).total;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = prm.n_tiles < sms ? prm.n_tiles : sms;
   switch (epi) {
     case DEPI_ONEBIT: return dense_launch<DEPI_ONEBIT>(prm, logd, grad, grid, smem, st);
@@ -615,4 +756,69 @@ extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, con
     case DEPI_LOGISTIC: return dense_launch<DEPI_LOGISTIC>(prm, logd, grad, grid, smem, st);
     default: return dense_launch<DEPI_STABLE>(prm, logd, grad, grid, smem, st);
   }
+}
+
+extern "C" int qmc_nll_fwd_bwd_dense(const float* S_dev, const float* C_dev, const uint8_t* code_dev,
+                                     const qmc_likelihood_t* lik, int IJ, int K, int R, double* nll_out_dev,
+                                     float* gS_out_dev, int64_t gs_row_stride, float* gC_out_dev, void* stream) {
+  return dense_entry(S_dev, C_dev, code_dev, lik, IJ, K, R, nll_out_dev, gS_out_dev, gs_row_stride, gC_out_dev, nullptr, stream);
+}
+
+// ---- fused exchange: regions and the entry point -----------------------------------------------------------------
+extern "C" int qmc_nll_fwd_bwd_dense_exchange(const float* S_dev, const float* C_dev, const uint8_t* code_dev,
+                                              const qmc_likelihood_t* lik, int IJ, int K, int R, double* nll_out_dev,
+                                              float* gS_out_dev, int64_t gs_row_stride, float* gC_out_dev,
+                                              const qmc_peer_exchange_t* px, void* stream) {
+  QMC_REQUIRE(px, "null exchange descriptor");
+  return dense_entry(S_dev, C_dev, code_dev, lik, IJ, K, R, nll_out_dev, gS_out_dev, gs_row_stride, gC_out_dev, px, stream);
+}
+
+extern "C" int64_t qmc_peer_region_bytes(int world, int slot_floats) {
+  if (world < 1 || world > QMC_PEER_MAX_WORLD || slot_floats < 4 || (slot_floats % 4) != 0) return 0;
+  return (int64_t)peer_slot_offset(world, slot_floats, 2, 0);
+}
+
+extern "C" int qmc_peer_alloc(int64_t bytes, void** region_out_dev, void* ipc_handle_out64) {
+  QMC_REQUIRE(region_out_dev && bytes >= (int64_t)sizeof(PeerHeader), "bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI promises a 64-byte handle");
+  void* p = nullptr;
+  QMC_CUDA_CHECK(cudaMalloc(&p, (size_t)bytes));
+  QMC_CUDA_CHECK(cudaMemset(p, 0, (size_t)bytes));
+  QMC_CUDA_CHECK(cudaDeviceSynchronize());
+  if (ipc_handle_out64) {
+    cudaIpcMemHandle_t h;
+    const cudaError_t err = cudaIpcGetMemHandle(&h, p);
+    if (err != cudaSuccess) {
+      cudaFree(p);
+      return set_error(QMC_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(err));
+    }
+    memcpy(ipc_handle_out64, &h, 64);
+  }
+  *region_out_dev = p;
+  return QMC_OK;
+}
+extern "C" int qmc_peer_open(const void* ipc_handle64, void** region_out_dev) {
+  QMC_REQUIRE(ipc_handle64 && region_out_dev, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle64, 64);
+  void* p = nullptr;
+  QMC_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *region_out_dev = p;
+  return QMC_OK;
+}
+extern "C" int qmc_peer_close(void* region_dev) {
+  if (region_dev) QMC_CUDA_CHECK(cudaIpcCloseMemHandle(region_dev));
+  return QMC_OK;
+}
+extern "C" int qmc_peer_free(void* region_dev) {
+  if (region_dev) QMC_CUDA_CHECK(cudaFree(region_dev));
+  return QMC_OK;
+}
+extern "C" int qmc_peer_status(const void* own_region_dev, int* status_out, void* stream) {
+  QMC_REQUIRE(own_region_dev && status_out, "null argument");
+  uint32_t st = 0;
+  QMC_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  QMC_CUDA_CHECK(cudaMemcpy(&st, (const uint8_t*)own_region_dev + offsetof(PeerHeader, status), 4, cudaMemcpyDeviceToHost));
+  *status_out = (int)st;
+  return QMC_OK;
 }

@@ -56,10 +56,69 @@ def pack_dense(Y: torch.Tensor, Wx: Optional[torch.Tensor], K: int) -> DenseObs:
     return DenseObs(code, IJ, K, nobs, max_level)
 
 
-def nll_fwd_bwd_dense(S2: torch.Tensor, C2: torch.Tensor, obs: DenseObs, lik: Likelihood, want_grad: bool = True, out=None):
+class PeerRegions:
+    """Exchange regions of the fused factor-gradient exchange (``qmc_nll_fwd_bwd_dense_exchange``): this rank's own
+    region (``qmc_peer_alloc``) and the peers' regions opened through CUDA IPC.  ``share`` is the host mechanism that
+    hands the 64-byte handles around: a callable ``handle_bytes -> list of every rank's handle bytes`` (default:
+    ``torch.distributed.all_gather_object``)."""
+
+    def __init__(self, rank: int, world: int, slot_floats: int, device, share=None):
+        if not 1 <= world <= _lib.QMC_PEER_MAX_WORLD:
+            raise ValueError(f"world {world}: the fused exchange supports 1..{_lib.QMC_PEER_MAX_WORLD} ranks")
+        self.rank, self.world, self.device = rank, world, torch.device(device)
+        self.slot_floats = (slot_floats + 3) // 4 * 4
+        nbytes = int(lib.qmc_peer_region_bytes(world, self.slot_floats))
+        own = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self._opened: list[int] = []
+        with torch.cuda.device(self.device):
+            check(lib.qmc_peer_alloc(nbytes, C.byref(own), handle))
+            self._own = own.value
+            if share is None:
+                import torch.distributed as dist
+
+                def share(h):
+                    got = [None] * world
+                    dist.all_gather_object(got, h)
+                    return got
+            handles = share(bytes(handle)) if world > 1 else [bytes(handle)]
+            self.px = _lib.PeerExchange()
+            self.px.rank, self.px.world, self.px.slot_floats = rank, world, self.slot_floats
+            for q in range(world):
+                if q == rank:
+                    self.px.region[q] = self._own
+                    continue
+                ptr = C.c_void_p()
+                check(lib.qmc_peer_open((C.c_ubyte * 64).from_buffer_copy(handles[q]), C.byref(ptr)))
+                self._opened.append(ptr.value)
+                self.px.region[q] = ptr.value
+
+    def status(self) -> int:
+        """0 = every exchange so far completed; 1 = a peer never arrived (the kernel gave up after ~2 s).  Synchronises
+        the current stream."""
+        st = C.c_int(0)
+        with torch.cuda.device(self.device):
+            check(lib.qmc_peer_status(self._own, C.byref(st), _stream()))
+        return st.value
+
+    def close(self):
+        """Every rank must have finished its last exchange (e.g. after a barrier) before any rank closes."""
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                check(lib.qmc_peer_close(p))
+            self._opened = []
+            if self._own:
+                check(lib.qmc_peer_free(self._own))
+                self._own = None
+
+
+def nll_fwd_bwd_dense(S2: torch.Tensor, C2: torch.Tensor, obs: DenseObs, lik: Likelihood, want_grad: bool = True, out=None,
+                      peers: Optional[PeerRegions] = None):
     """``S2 [R, IJ]``, ``C2 [R, K]`` fp32 CUDA.  Returns (nll fp64 0-dim, gS [R, IJ], gC [R, K]).
     ``out=(nll fp64 [1], gS, gC)`` writes into existing buffers; gS may then be a column slice of a wider
-    row-major buffer (row stride >= IJ, unit column stride), gC must be contiguous."""
+    row-major buffer (row stride >= IJ, unit column stride), gC must be contiguous.
+    ``peers``: this rank evaluates its pixel block of a sharded instance and the kernel itself exchanges the partial
+    gC and NLL with the peer ranks over NVLink: nll and gC come back summed over all ranks (same bits everywhere)."""
     if not (S2.is_cuda and C2.is_cuda):
         raise ValueError("nll_fwd_bwd_dense needs CUDA tensors: there is no CPU path")
     R, IJ = S2.shape
@@ -83,8 +142,15 @@ def nll_fwd_bwd_dense(S2: torch.Tensor, C2: torch.Tensor, obs: DenseObs, lik: Li
             nll = torch.empty(1, dtype=torch.float64, device=S2.device)
             gS = torch.empty_like(S2) if want_grad else None
             gC = torch.empty_like(C2) if want_grad else None
-        check(lib.qmc_nll_fwd_bwd_dense(S2.data_ptr(), C2.data_ptr(), obs.code.data_ptr(), C.byref(lik), IJ, K, R,
-                                        nll.data_ptr(), gS.data_ptr() if want_grad else None,
-                                        gS.stride(0) if want_grad else 0,
-                                        gC.data_ptr() if want_grad else None, _stream()))
+        if peers is not None:
+            if not want_grad:
+                raise ValueError("the fused exchange combines gradients: want_grad=False is not supported with it")
+            check(lib.qmc_nll_fwd_bwd_dense_exchange(S2.data_ptr(), C2.data_ptr(), obs.code.data_ptr(), C.byref(lik), IJ, K, R,
+                                                     nll.data_ptr(), gS.data_ptr(), gS.stride(0), gC.data_ptr(),
+                                                     C.byref(peers.px), _stream()))
+        else:
+            check(lib.qmc_nll_fwd_bwd_dense(S2.data_ptr(), C2.data_ptr(), obs.code.data_ptr(), C.byref(lik), IJ, K, R,
+                                            nll.data_ptr(), gS.data_ptr() if want_grad else None,
+                                            gS.stride(0) if want_grad else 0,
+                                            gC.data_ptr() if want_grad else None, _stream()))
     return nll.reshape(-1)[0], gS, gC

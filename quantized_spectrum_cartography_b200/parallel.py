@@ -16,7 +16,10 @@ Two cases, matching how the path shards:
     ``[gS | gC | nll]`` buffer, 4*(R*IJ + R*K + 2) bytes (16.8 MB at cfg4); the tcgen05 kernel writes its pixel
     block of gS, its gC and its NLL straight into that persistent buffer;
   - ``"pixel_block"`` -- all-reduce only ``[gC | nll]`` (16 KB at cfg4) and, if the caller wants the
-    full gS everywhere, all-gather the disjoint gS slices.
+    full gS everywhere, all-gather the disjoint gS slices.  With ``exchange="peer"`` (dense tcgen05 kernel, one
+    node, at most 8 ranks) there is no collective call at all: the kernel's last CTA pushes the rank's partial
+    ``[gC | nll]`` into every peer's exchange region with plain stores over NVLink and sums the peers' slots
+    (``qmc_nll_fwd_bwd_dense_exchange``, csrc/qmc_dense.cu).
 
 The local evaluation is injectable (``local_eval``) so that the host-side logic -- partitioning,
 packing, the collective, unpacking -- runs under ``gloo`` on CPU in the tests with the checker as
@@ -130,6 +133,8 @@ class ShardedInstance:
     mode: str = "flat"
     local_eval: Callable = _cuda_local_eval
     align: int = 1
+    exchange: str = "nccl"                    # "nccl" (torch.distributed all-reduce) | "peer" (fused into the dense kernel)
+    _peers: object = None
     _buf: Optional[torch.Tensor] = None      # persistent exchange buffer (fp32): [gS | gC | nll_hi, nll_lo]
     _nll64: Optional[torch.Tensor] = None
     _graph: object = None
@@ -139,12 +144,14 @@ class ShardedInstance:
     @classmethod
     def from_dense(cls, Y, Wx, K: int, R: int, lik, *, mode: str = "flat", device=None, align: int = 1,
                    dense: Optional[bool] = None, build: Optional[Callable] = None,
-                   local_eval: Callable = _cuda_local_eval) -> "ShardedInstance":
+                   local_eval: Callable = _cuda_local_eval, exchange: str = "nccl") -> "ShardedInstance":
         """``Y``/``Wx``: the full instance ``[K, IJ]`` (reference layout ``[K,1,I,J]`` accepted); each
         rank keeps only its pixel block.  ``dense``: use the tcgen05 dense kernel for the local block
         (default: when the geometry is supported and at least a quarter of the entries are observed)."""
         if mode not in ("flat", "pixel_block"):
             raise ValueError(mode)
+        if exchange not in ("nccl", "peer") or (exchange == "peer" and mode != "pixel_block"):
+            raise ValueError(f"exchange={exchange!r} with mode={mode!r}: the fused exchange carries [gC | nll] only")
         rank, world = _world()
         Yk = Y.reshape(K, -1)
         IJ = Yk.shape[1]
@@ -159,7 +166,12 @@ class ShardedInstance:
             obs = pack_dense(Yl, Wl, K) if dense else make_obs(Yl, Wl, K, device, B=1, R=R, tiled=False)
         else:
             obs = build(Yl, Wl)
-        return cls(IJ, K, R, lo, hi, obs, lik, mode, local_eval, align)
+        if exchange == "peer":
+            from .dense import DenseObs
+            if local_eval is not _cuda_local_eval or not isinstance(obs, DenseObs):
+                raise ValueError('exchange="peer" is part of the dense tcgen05 kernel: it needs a supported geometry '
+                                 "and the CUDA evaluator")
+        return cls(IJ, K, R, lo, hi, obs, lik, mode, local_eval, align, exchange)
 
     def flat_size(self) -> int:
         """Elements of the contract-form exchange buffer [gS | gC | nll] (the NLL travels as two fp32 words,
@@ -168,6 +180,21 @@ class ShardedInstance:
 
     def exchange_bytes(self) -> int:
         return 4 * (self.flat_size() if self.mode == "flat" else self.R * self.K + 2)
+
+    def exchange_status(self) -> int:
+        """Fused exchange only: 0 = fine, 1 = a peer never arrived in some evaluation (results are partial sums)."""
+        return 0 if self._peers is None else self._peers.status()
+
+    def close(self):
+        """Release the exchange regions (all ranks, after their last evaluation)."""
+        if self._peers is not None:
+            torch.cuda.synchronize()
+            _, world = _world()
+            if world > 1:
+                dist.barrier()
+            self._peers.close()
+            self._peers = None
+            self._graph = None
 
     # ---- one evaluation: local kernel into the persistent buffer, one collective ---------------------------
     def _local_into(self, buf, Sl, C, off_gs):
@@ -182,7 +209,7 @@ class ShardedInstance:
             if isinstance(self.obs, DenseObs):
                 gS_view = (buf[: R * IJ].view(R, IJ)[:, self.lo:self.hi] if self.mode == "flat" else
                            buf[: R * n].view(R, n))
-                nll_fwd_bwd_dense(Sl, C, self.obs, self.lik, out=(self._nll64, gS_view, gC_view))
+                nll_fwd_bwd_dense(Sl, C, self.obs, self.lik, out=(self._nll64, gS_view, gC_view), peers=self._peers)
                 direct = True
         if not direct:
             nll, gSl, gC = self.local_eval(Sl.unsqueeze(0), C.reshape(1, R, K), self.obs, self.lik, True)
@@ -192,6 +219,8 @@ class ShardedInstance:
                 buf[: R * n].view(R, n).copy_(gSl.reshape(R, -1))
             gC_view.copy_(gC.reshape(R, K))
             self._nll64.copy_(nll.reshape(1).to(torch.float64))
+        if self._peers is not None:
+            return                           # the kernel left the global sums in place: nothing travels through `tail`
         hi32 = self._nll64.to(torch.float32)
         tail[0:1].copy_(hi32)
         tail[1:2].copy_((self._nll64 - hi32.to(torch.float64)).to(torch.float32))
@@ -207,7 +236,7 @@ class ShardedInstance:
                 dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         else:
             self._local_into(buf, Sl, C, R * n)
-            if world > 1:
+            if world > 1 and self._peers is None:
                 dist.all_reduce(buf[R * n:], op=dist.ReduceOp.SUM)
 
     def evaluate(self, S, C, gather_gS: bool = True, cuda_graph: bool = False):
@@ -232,6 +261,9 @@ class ShardedInstance:
             self._buf = torch.zeros(size, dtype=torch.float32, device=dev)
             self._nll64 = torch.zeros(1, dtype=torch.float64, device=dev)
             self._graph = None
+        if self.exchange == "peer" and self._peers is None:
+            from .dense import PeerRegions
+            self._peers = PeerRegions(rank, world, R * K + 2, dev)   # collective: the ranks swap IPC handles
         if cuda_graph and dev.type == "cuda":
             # The graph is captured ONCE per instance, on staging buffers the instance owns: whether a rank
             # re-captures must not depend on where its allocator happened to put the caller's tensors (a rank that
@@ -254,7 +286,10 @@ class ShardedInstance:
         buf = self._buf
         off = R * IJ if self.mode == "flat" else R * n
         gC_all = buf[off: off + R * K].view(R, K)
-        nll = buf[off + R * K].to(torch.float64) + buf[off + R * K + 1].to(torch.float64)
+        if self._peers is not None:
+            nll = self._nll64[0].clone()
+        else:
+            nll = buf[off + R * K].to(torch.float64) + buf[off + R * K + 1].to(torch.float64)
         if self.mode == "flat":
             return nll, buf[: R * IJ].view(R, IJ), gC_all
         gSl = buf[: R * n].view(R, n)

@@ -780,6 +780,42 @@ def test_dense_tcgen05_path_vs_oracle_and_gather(q, IJ, K, R, levels, log_domain
     assert nll_f.item() == pytest.approx(nll.item(), rel=1e-12)
 
 
+def test_dense_fused_exchange_single_rank(q):
+    """qmc_nll_fwd_bwd_dense_exchange with a world of one rank: the last CTA's exchange (own slot, flag, sum) must give
+    back exactly what the plain entry gives, call after call (epoch parity) and under CUDA-graph replay (the epoch
+    lives in device memory).  The two-rank case over NVLink runs in tests/test_gpu_multi.py."""
+    from quantized_spectrum_cartography_b200 import dense
+    IJ, K, R = 40000, 128, 8      # 313 tiles: several rounds of the persistent CTAs
+    S, C, Y, Wx, bb, sigma, off = _random_instance(1, IJ, 1, K, R, 0.5, 4, seed=11)
+    lik = q.make_likelihood(bb, sigma, offset=off)
+    dobs = dense.pack_dense(Y[0].cuda(), Wx[0].cuda(), K)
+    Sd, Cd = S[0].cuda(), C[0].cuda()
+    nll0, gS0, gC0 = dense.nll_fwd_bwd_dense(Sd, Cd, dobs, lik)
+    peers = dense.PeerRegions(0, 1, R * K + 2, "cuda")
+    try:
+        for _ in range(3):
+            nll, gS, gC = dense.nll_fwd_bwd_dense(Sd, Cd, dobs, lik, peers=peers)
+            assert nll.item() == pytest.approx(nll0.item(), rel=1e-9)
+            assert torch.equal(gS, gS0)
+            assert rel_err(gC.cpu().numpy(), gC0.cpu().numpy()) < 1e-5    # atomics: order of the CTAs' additions
+        out = (torch.zeros(1, dtype=torch.float64, device="cuda"), torch.empty_like(Sd), torch.empty_like(Cd))
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            dense.nll_fwd_bwd_dense(Sd, Cd, dobs, lik, out=out, peers=peers)
+        for _ in range(4):
+            out[2].fill_(7.0)
+            g.replay()
+            torch.cuda.synchronize()
+            assert out[0].item() == pytest.approx(nll0.item(), rel=1e-9)
+            assert rel_err(out[2].cpu().numpy(), gC0.cpu().numpy()) < 1e-5
+        assert peers.status() == 0
+        with pytest.raises(ValueError, match="want_grad"):
+            dense.nll_fwd_bwd_dense(Sd, Cd, dobs, lik, want_grad=False, peers=peers)
+    finally:
+        peers.close()
+
+
 def test_dense_path_rejects_what_it_cannot_run(q):
     from quantized_spectrum_cartography_b200 import _lib, dense
     assert not dense.dense_supported(100, 4) and not dense.dense_supported(512, 4) and not dense.dense_supported(64, 17)

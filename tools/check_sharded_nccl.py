@@ -46,10 +46,12 @@ def run():
         C = maps.C_true[0].contiguous()
         obs_all = q.build_obs(Y, Wx, K, IJ, 1)
         ref = q.nll_fwd_bwd(S.unsqueeze(0), C.unsqueeze(0), obs_all, lik, algo=_lib.QMC_ALGO_FLAT)   # single-GPU truth
-        for use_dense in (True, False):
-            for mode in ("flat", "pixel_block"):
+        for use_dense, mode, exchange in ((True, "flat", "nccl"), (True, "pixel_block", "nccl"), (True, "pixel_block", "peer"),
+                                          (False, "flat", "nccl"), (False, "pixel_block", "nccl")):
+            if True:
                 for graph in (False, True):
-                    inst = parallel.ShardedInstance.from_dense(Y, Wx, K, R, lik, mode=mode, align=128, dense=use_dense)
+                    inst = parallel.ShardedInstance.from_dense(Y, Wx, K, R, lik, mode=mode, align=128, dense=use_dense,
+                                                               exchange=exchange)
                     assert isinstance(inst.obs, dense.DenseObs) == use_dense
                     for _ in range(2):                                      # the second call replays / reuses buffers
                         nll, gS, gC = inst.evaluate(S, C, cuda_graph=graph)
@@ -63,7 +65,21 @@ def run():
                     got = gS_loc if mode == "pixel_block" else gS_loc[:, inst.lo:inst.hi]
                     assert float((got - want).norm() / want.norm()) < 1e-4
                     assert abs(nll2.item() / ref[0][0].item() - 1) < 1e-5
-                    out[f"{name}_{'dense' if use_dense else 'gather'}_{mode}_{'graph' if graph else 'eager'}"] = e
+                    tag = f"{name}_{'dense' if use_dense else 'gather'}_{mode}_{'graph' if graph else 'eager'}"
+                    if exchange == "peer":
+                        # the kernel's own exchange over NVLink peer memory: no collective call; every rank must hold
+                        # the same bits (slots are added in rank order), across repeated evaluations (epoch parity)
+                        for _ in range(5):
+                            nll3, _, gC3 = inst.evaluate(S[:, inst.lo:inst.hi], C, gather_gS=False, cuda_graph=graph)
+                        assert inst.exchange_status() == 0
+                        mine = torch.cat([gC3.reshape(-1).double(), nll3.reshape(1)])
+                        both = [torch.empty_like(mine) for _ in range(world)]
+                        dist.all_gather(both, mine)
+                        assert all(torch.equal(b, both[0]) for b in both), "ranks disagree bitwise"
+                        assert float((gC3 - ref[2][0]).norm() / ref[2][0].norm()) < 1e-4
+                        inst.close()
+                        tag += "_peer"
+                    out[tag] = e
     # batched maps: contiguous chunks, no collective on the data path
     B = 6
     lo, hi = parallel.partition_maps(B, world, rank)
