@@ -99,6 +99,25 @@ __device__ __forceinline__ BinEval probit_bin_stable(float lo, float hi, float x
   const float rl = erfcx_pos<FAST>(wl), ru = erfcx_pos<FAST>(wu);
   const float gscale = inv_a * kInvSqrtPi;
   BinEval o;
+  if (FAST) {
+    // Branch-free form for the throughput kernels (neighbouring entries fall on different sides of their bins, so a
+    // warp would walk both branches anyway): the tail and the straddling case share the reciprocals of erfcx, one
+    // exponential (D or El), the logarithm and the final reciprocal; same operations, hence the same bits, as the
+    // branches below.
+    const bool right = zl >= 0.0f, tail = right || zu <= 0.0f;
+    const float n = right ? wl : wu, f = right ? wu : wl;
+    const float rn = right ? rl : ru, rf = right ? ru : rl;
+    const float Ea = ex2_approx((tail ? (n - f) * (n + f) : -wl * wl) * kLog2e);   // D (tail) or El (straddle)
+    const float Eu = ex2_approx((-wu * wu) * kLog2e);
+    const float core = 0.5f * fmaf(-Ea, rf, rn);
+    const float P = 1.0f - 0.5f * fmaf(Ea, rl, Eu * ru);
+    const float arg = tail ? core : P;
+    const float l = lg2_approx(arg) * kLn2;
+    o.logp = tail ? fmaf(-n, n, l) : l;
+    const float v = (tail ? 1.0f - Ea : Eu - Ea) * rcp_approx(arg);
+    o.gx = ((tail && right) ? -v : v) * gscale;
+    return o;
+  }
   if (zl >= 0.0f || zu <= 0.0f) {
     const bool right = zl >= 0.0f;
     const float n = right ? wl : wu, f = right ? wu : wl;

@@ -5,7 +5,8 @@
 // kernels (qmc/quantization_model.py:22-39,57-61,70-86; qmc/qmc.ipynb c1:145-153).
 //
 // Per CTA (256 threads, persistent over 128-pixel tiles):
-//   MMA1  D1[128 px x K bands]  = S_tile * C^T          kind::tf32, 3xTF32 split (hi*hi + hi*lo + lo*hi)
+//   MMA1  D1[128 px x K bands]  = S_tile * C^T          kind::tf32, 3xTF32 split (hi*hi + hi*lo + lo*hi: three
+//         descriptor walks over the same [Sh|Sl] and [Ch|Cl] operand tiles)
 //   epilogue (8 warps): tcgen05.ld a 32-column slab of D1 per thread, read the 1-byte codes of the
 //         same entries, evaluate log P and g, store g (hi/lo TF32 parts) into shared memory twice:
 //         G[128 px x 32 bands] with bands contiguous and G^T[32 bands x 128 px] with pixels contiguous,
@@ -15,6 +16,9 @@
 //   MMA3  D3[32(64) bands x 16] += G^T * S_tile          (gC block; M = 64 instruction, rows 32..63 unused)
 // D2 is written to gS after the last band block of a tile, D3 accumulates over all tiles of the CTA
 // and is added to gC once at the end.
+// A tcgen05.mma of these shapes costs ~65 cycles whatever its size (measured: tools/dense_probe.py), so the 48
+// instructions of MMA3 are a 1.6 us chain per band block: the G^T operand is double-buffered and MMA3 of block b runs
+// under the likelihood arithmetic of block b+1 (MMA2, 12 instructions, keeps a single G buffer).
 //
 // Observation format: one byte per dense entry, pixel-major code8[IJ][K], 255 = not observed
 // (qmc_dense_pack builds it from the reference's Y / Wx).
@@ -29,6 +33,12 @@ constexpr int DT_THREADS = 512;   // 16 epilogue warps: 4 per TMEM lane quadrant
 constexpr int DT_LAUNCH = DT_THREADS + 32;   // + one warp that only issues the tensor-core instructions
 constexpr int DT_SLAB = DT_BLK / (DT_THREADS / 128);
 constexpr uint32_t TMEM_COLS = 512;
+#ifndef QMC_DENSE_NCH
+#define QMC_DENSE_NCH 4
+#endif
+#ifndef QMC_DENSE_NCH_ALT
+#define QMC_DENSE_NCH_ALT 2
+#endif
 constexpr uint32_t COL_D2 = 256, COL_D3 = 272;
 
 struct DenseParams {
@@ -43,6 +53,7 @@ struct DenseParams {
   int tile_pix;          // pixels a tile really holds (<= DT_PIX; the rest of the 128 TMEM lanes idles), chosen by the host so
                          // that the tiles divide evenly over the persistent CTAs
   int n_bounds, one_sided;
+  int debug;             // measurement hook (QMC_DENSE_DEBUG): 1 skip MMA3, 2 skip MMA2, 4 skip the likelihood, 8 skip the G stores
   float inv_a, offset, thr;
   // fused factor-gradient exchange of a sharded instance (px_world == 0: none); see peer_exchange()
   int px_rank, px_world, px_slot_floats;
@@ -157,15 +168,24 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N, bool a_mn_majo
   return (1u << 4) /*D = f32*/ | (2u << 7) /*A = tf32*/ | (2u << 10) /*B = tf32*/ |
          ((a_mn_major ? 1u : 0u) << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Both are executed by the WHOLE issuing warp, converged; one elected lane issues the instruction.  The operands are
+// then warp-uniform values the compiler keeps in uniform registers: an MMA costs two or three uniform integer
+// instructions plus UTCHMMA.  (Issued from inside an `if (lane == 0)` branch instead, every operand went through an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop: ~12 dependent instructions, ~115 cycles per MMA -- the issuing thread,
+// not the tensor pipe, bounded the kernel.)
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(s_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -220,6 +240,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load in two halves: issue (the registers are written asynchronously) and wait (the registers pass through
+// the wait as read-write operands, so nothing that uses them can be scheduled above it)
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_wait(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :: "memory");
+}
+
 // TF32 split: hi keeps the 10 explicit mantissa bits the tensor core reads, lo is the exact rest
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
@@ -255,21 +288,25 @@ __device__ __forceinline__ BinEval dense_eval(const DenseParams& prm, const floa
 }
 
 // Shared memory map (bytes).  All operand regions are 128-byte aligned.
-//   A1  : S tile split, K-major [chunk j][pixel][16 B], chunks = 3*Rp8/4          128*16*chunks
-//   B1  : C split,      K-major [chunk j][band ][16 B]                             K*16*chunks
+//   A1  : S tile split [Sh|Sl], K-major [chunk j][pixel][16 B], chunks = 2*Rp8/4   128*16*chunks
+//   B1  : C split [Ch|Cl],      K-major [chunk j][band ][16 B]                     K*16*chunks
 //   B2h/B2l : C as [chunk of 4 bands][r-group][r%8][16 B]  (N = 16, K-major)       K/4*256 each
 //   B3h/B3l : S tile as [chunk of 4 pixels][r-group][r%8][16 B]                    32*256 each
 //   Gh/Gl   : g block  [chunk of 4 bands][pixel][16 B]                             8*2048 each
 //   GTh/GTl : g block transposed [chunk of 4 pixels][band][16 B], chunk pitch 528 B (32 rows + 16 B of
-//             padding so that the scalar stores of 32 consecutive pixels hit 32 different banks), plus
-//             512 B of slack because the M = 64 instruction reads 64 rows per chunk
-//   queue   : per warp 32 x DT_SLAB (value, code) pairs: the observed entries of a warp's slab, compacted
+//             padding so that the scalar stores of 32 consecutive pixels hit 32 different banks); two buffers
+//             (even / odd band blocks), and 512 B of slack behind the last one because the M = 64 instruction
+//             reads 64 rows per chunk
+//   queue   : per warp 32 x DT_SLAB values (fp32) and as many codes (bytes): the observed entries of a warp's
+//             slab, compacted
 constexpr uint32_t GT_PITCH = 528;
+constexpr uint32_t GT_BYTES = 32 * GT_PITCH;   // one G^T operand (hi or lo) of one band block
+constexpr uint32_t QUEUE_WARP_BYTES = 32 * DT_SLAB * 5;
 struct DenseSmem {
-  uint32_t a1, b1, b2h, b2l, b3h, b3l, gh, gl, gth, gtl, queue, total;
+  uint32_t a1, b1, b2h, b2l, b3h, b3l, gh, gl, gt, queue, total;   // gt: [buffer 0: h, l][buffer 1: h, l][slack]
 };
 __host__ __device__ inline DenseSmem dense_smem_map(int K, int Rp8) {
-  const uint32_t chunks = 3 * Rp8 / 4;
+  const uint32_t chunks = 2 * Rp8 / 4;
   DenseSmem m;
   uint32_t o = 0;
   m.a1 = o; o += DT_PIX * 16 * chunks;
@@ -280,25 +317,28 @@ __host__ __device__ inline DenseSmem dense_smem_map(int K, int Rp8) {
   m.b3l = o; o += 32 * 256;
   m.gh = o; o += 8 * 2048;
   m.gl = o; o += 8 * 2048;
-  m.gth = o; o += 32 * GT_PITCH + 512;
-  m.gtl = o; o += 32 * GT_PITCH + 512;
-  m.queue = o; o += (DT_THREADS / 32) * (32 * DT_SLAB) * 8;   // per warp: 32 lanes x DT_SLAB (value, code) pairs
+  m.gt = o; o += 4 * GT_BYTES + 512;
+  m.queue = o; o += (DT_THREADS / 32) * QUEUE_WARP_BYTES;
   m.total = o;
   return m;
 }
 
-template <int EPI, bool LOGD, bool GRAD>
+// NCH: independent likelihood evaluations per lane and pass of the compacted queue (instruction-level parallelism for
+// the ~17 warps of the CTA: 4 passes a slab's ~128 observed entries in one go)
+template <int EPI, bool LOGD, bool GRAD, int NCH>
 __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams prm) {
   extern __shared__ __align__(1024) uint8_t dsm[];
-  __shared__ uint64_t bar1, bar2, gfull;
+  __shared__ uint64_t bar1, bar2, bar3[2], gfull;
   __shared__ uint32_t tmem_base_sh;
   __shared__ double wsum[DT_LAUNCH / 32];
   __shared__ float bnd[QMC_MAX_BOUNDS + 1];
 
   const int K = prm.K, R = prm.R, Rp8 = prm.Rp8;
-  const int chunks1 = 3 * Rp8 / 4;
+  const int chunks1 = 2 * Rp8 / 4;
   const DenseSmem map = dense_smem_map(K, Rp8);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // (the warp index through a shuffle: the compiler then knows it is the same in all lanes, and the issuing warp's
+  //  branch is warp-uniform code that may use the uniform datapath)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant, which 8-band slab of a 32-band block
   // Warp specialisation: warps 0..15 evaluate the likelihood and write the G operands; warp 16 issues every
   // tcgen05.mma.  The epilogue warps hand a block's G over through the `gfull` mbarrier and go straight on to the next
@@ -316,6 +356,8 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
   if (tid == 0) {
     dmbar_init(&bar1, 1);
     dmbar_init(&bar2, 1);
+    dmbar_init(&bar3[0], 1);
+    dmbar_init(&bar3[1], 1);
     dmbar_init(&gfull, DT_THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -329,7 +371,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
       ch[r] = tf32_hi(c);
       cl[r] = c - ch[r];
     }
-    // B1 row = band k, elements [Ch(0..Rp8) | Cl | Ch]
+    // B1 row = band k, elements [Ch(0..Rp8) | Cl]
     for (int j = 0; j < chunks1; ++j) {
       const int e = 4 * j, seg = e / Rp8, r0 = e % Rp8;
       const float* src = (seg == 1) ? cl : ch;
@@ -355,7 +397,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
 
   float nll_part = 0.0f;   // per tile (<= 256 terms) in fp32, folded into nll_acc in fp64 after every tile
   double nll_acc = 0.0;
-  uint32_t ph1 = 0, ph2 = 0, phg = 0;
+  uint32_t ph1 = 0, ph2 = 0, ph3[2] = {0, 0}, phg = 0;
   bool d3_started = false;   // D3 blocks accumulate over all tiles of this CTA
   const int nblk = K / DT_BLK;
   const bool short_tile = prm.tile_pix < DT_PIX;
@@ -389,7 +431,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
           *reinterpret_cast<float*>(dsm + map.b3l + o) = sl[i];
         }
       }
-      // A1 row = pixel p, elements [Sh | Sh | Sl]; this thread owns ranks rh*8 .. rh*8+7 (if < Rp8)
+      // A1 row = pixel p, elements [Sh | Sl]; this thread owns ranks rh*8 .. rh*8+7 (if < Rp8)
       if (rh * 8 < Rp8) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -398,22 +440,24 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
           const float4 l4 = make_float4(sl[4 * q], sl[4 * q + 1], sl[4 * q + 2], sl[4 * q + 3]);
           const int per = Rp8 / 4;
           *reinterpret_cast<float4*>(dsm + map.a1 + (size_t)(jr) * 2048 + p * 16) = h4;
-          *reinterpret_cast<float4*>(dsm + map.a1 + (size_t)(per + jr) * 2048 + p * 16) = h4;
-          *reinterpret_cast<float4*>(dsm + map.a1 + (size_t)(2 * per + jr) * 2048 + p * 16) = l4;
+          *reinterpret_cast<float4*>(dsm + map.a1 + (size_t)(per + jr) * 2048 + p * 16) = l4;
         }
       }
     }
     fence_async();
     tc_fence_before();
     __syncthreads();
-    // ---- MMA1: D1 = [Sh|Sh|Sl] * [Ch|Cl|Ch]^T ------------------------------------------------------
-    if (issuer && lane == 0) {
+    // ---- MMA1: D1 = Sh*Ch^T + Sh*Cl^T + Sl*Ch^T ---------------------------------------------------
+    if (issuer) {
       tc_fence_after();
-      const int ksteps = 3 * Rp8 / 8;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t ad = umma_desc(sbase + map.a1 + ks * 2 * 2048, 2048, 128);
-        const uint64_t bd = umma_desc(sbase + map.b1 + ks * 2 * K * 16, K * 16, 128);
-        umma_tf32(tmem, ad, bd, idesc1, ks > 0);
+      const int per = Rp8 / 4;   // 16-byte chunks per segment
+      for (int term = 0; term < 3; ++term) {
+        const int aseg = term == 2 ? per : 0, bseg = term == 1 ? per : 0;
+        for (int kk = 0; kk < Rp8 / 8; ++kk) {
+          const uint64_t ad = umma_desc(sbase + map.a1 + (aseg + kk * 2) * 2048, 2048, 128);
+          const uint64_t bd = umma_desc(sbase + map.b1 + (bseg + kk * 2) * K * 16, K * 16, 128);
+          umma_tf32(tmem, ad, bd, idesc1, (term | kk) != 0);
+        }
       }
       umma_commit(&bar1);
     }
@@ -423,41 +467,54 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
     }
     ph1 ^= 1;
 
-    // ---- epilogue, one 64-band block at a time ------------------------------------------------------
+    // ---- epilogue, one 32-band block at a time ------------------------------------------------------
+    // a warp's slab of D1 is loaded one block ahead of its use: the TMEM round trip hides behind a block's arithmetic
+    uint32_t xnext[DT_SLAB];
+    if (!issuer) tmem_ld8_issue(tlane + (uint32_t)(half * DT_SLAB), xnext);
     for (int blk = 0; blk < nblk; ++blk) {
       if (issuer) {
-        if (GRAD && lane == 0) {
+        if (GRAD) {
           dmbar_wait(&gfull, phg);   // all sixteen epilogue warps have written this block's G operands
           tc_fence_after();
-          // MMA2: D2[128 x 16] += G_blk * C_blk   (K = 32 bands of this block, 4 steps of 8)
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t ga = (term == 2) ? map.gl : map.gh;
-            const uint32_t cb = (term == 1) ? map.b2l : map.b2h;
-            for (int ks = 0; ks < DT_BLK / 8; ++ks) {
-              const uint64_t ad = umma_desc(sbase + ga + ks * 2 * 2048, 2048, 128);
-              const uint64_t bd = umma_desc(sbase + cb + (blk * (DT_BLK / 4) + ks * 2) * 256, 256, 128);
-              umma_tf32(tmem + COL_D2, ad, bd, idesc2, (blk | term | ks) != 0);
+          // MMA2: D2[128 x 16] += G_blk * C_blk   (K = 32 bands of this block, 4 steps of 8).  A descriptor's start
+          // address field counts 16-byte units: stepping through an operand is an add on the descriptor.
+          if (!(prm.debug & 2)) {
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+              const uint64_t ad0 = umma_desc(sbase + ((term == 2) ? map.gl : map.gh), 2048, 128);
+              const uint64_t bd0 = umma_desc(sbase + ((term == 1) ? map.b2l : map.b2h) + blk * (DT_BLK / 4) * 256, 256, 128);
+#pragma unroll
+              for (int ks = 0; ks < DT_BLK / 8; ++ks)
+                umma_tf32(tmem + COL_D2, ad0 + (uint64_t)(ks * 2 * 2048 / 16), bd0 + (uint64_t)(ks * 2 * 256 / 16), idesc2,
+                          (blk | term | ks) != 0);
             }
           }
+          umma_commit(&bar2);   // the G buffer is free again
           // MMA3: D3_blk[bands x 16] += G_blk^T * S_tile   (K = 128 pixels, 16 steps of 8; M = 64
           // instruction whose rows 32..63 read the following chunk and are never looked at)
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t ga = (term == 2) ? map.gtl : map.gth;
-            const uint32_t sb = (term == 1) ? map.b3l : map.b3h;
-            for (int ks = 0; ks < DT_PIX / 8; ++ks) {
-              const uint64_t ad = umma_desc(sbase + ga + ks * 2 * GT_PITCH, GT_PITCH, 128);
-              const uint64_t bd = umma_desc(sbase + sb + ks * 2 * 256, 256, 128);
-              umma_tf32(tmem + COL_D3 + blk * DT_RP, ad, bd, idesc3, d3_started || (term | ks) != 0);
+          const uint32_t gtb = map.gt + (uint32_t)(blk & 1) * 2 * GT_BYTES;
+          if (!(prm.debug & 1)) {
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+              const uint64_t ad0 = umma_desc(sbase + ((term == 2) ? gtb + GT_BYTES : gtb), GT_PITCH, 128);
+              const uint64_t bd0 = umma_desc(sbase + ((term == 1) ? map.b3l : map.b3h), 256, 128);
+#pragma unroll
+              for (int ks = 0; ks < DT_PIX / 8; ++ks)
+                umma_tf32(tmem + COL_D3 + blk * DT_RP, ad0 + (uint64_t)(ks * 2 * GT_PITCH / 16), bd0 + (uint64_t)(ks * 2 * 256 / 16),
+                          idesc3, d3_started || (term | ks) != 0);
             }
           }
-          umma_commit(&bar2);
+          umma_commit(&bar3[blk & 1]);   // this block's G^T buffer is free again
         }
         phg ^= 1;
         continue;
       }
       const int k0 = blk * DT_BLK + half * DT_SLAB;   // first band of this thread's 8-column slab
       float x[DT_SLAB];
-      tmem_ld8(tlane + (uint32_t)k0, x);
+      tmem_ld8_wait(xnext);
+#pragma unroll
+      for (int i = 0; i < DT_SLAB; ++i) x[i] = __uint_as_float(xnext[i]);
+      if (blk + 1 < nblk) tmem_ld8_issue(tlane + (uint32_t)(k0 + DT_BLK), xnext);
       uint32_t cw[DT_SLAB / 4];
       cw[0] = cnext.x; cw[1] = cnext.y;
       if (inside && blk + 1 < nblk) cnext = __ldg(reinterpret_cast<const uint2*>(crow + k0 + DT_BLK));
@@ -477,32 +534,48 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         const int base = incl - cnt;
-        uint2* q = reinterpret_cast<uint2*>(dsm + map.queue) + warp * (32 * DT_SLAB);
+        float* qv = reinterpret_cast<float*>(dsm + map.queue + warp * QUEUE_WARP_BYTES);
+        uint8_t* qc = reinterpret_cast<uint8_t*>(qv + 32 * DT_SLAB);
         int w = base;
 #pragma unroll
         for (int i = 0; i < DT_SLAB; ++i) {
           const uint32_t code = (cw[i >> 2] >> (8 * (i & 3))) & 0xffu;
-          if (code != 255u) q[w++] = make_uint2(__float_as_uint(x[i]), code);
+          if (code != 255u) {
+            qv[w] = x[i];
+            qc[w++] = (uint8_t)code;
+          }
         }
         __syncwarp();
-        for (int id = lane; id < total; id += 64) {   // two entries per lane and pass: independent chains for the scheduler
-          if (id - lane + 32 >= total) {              // (warp-uniform) at most 32 entries left: a single evaluation each
-            const uint2 e0 = q[id];
-            float d0;
-            const BinEval v0 = dense_eval<EPI, LOGD>(prm, bnd, __uint_as_float(e0.x), (int)e0.y, d0);
-            nll_part -= v0.logp;
-            q[id].x = __float_as_uint(v0.gx * d0);
+        for (int id0 = 0; id0 < ((prm.debug & 4) ? 0 : total); id0 += 32 * NCH) {   // warp-uniform; NCH entries per lane and pass
+          const int rem = total - id0;
+          if (rem <= 32) {                                  // at most 32 entries left: a single evaluation each
+            if (lane < rem) {
+              float d0;
+              const BinEval v0 = dense_eval<EPI, LOGD>(prm, bnd, qv[id0 + lane], (int)qc[id0 + lane], d0);
+              nll_part -= v0.logp;
+              qv[id0 + lane] = v0.gx * d0;
+            }
             break;
           }
-          const bool two = id + 32 < total;
-          const uint2 e0 = q[id];
-          const uint2 e1 = two ? q[id + 32] : e0;
-          float d0, d1;
-          const BinEval v0 = dense_eval<EPI, LOGD>(prm, bnd, __uint_as_float(e0.x), (int)e0.y, d0);
-          const BinEval v1 = dense_eval<EPI, LOGD>(prm, bnd, __uint_as_float(e1.x), (int)e1.y, d1);
-          nll_part -= v0.logp + (two ? v1.logp : 0.0f);
-          q[id].x = __float_as_uint(v0.gx * d0);
-          if (two) q[id + 32].x = __float_as_uint(v1.gx * d1);
+          float ev[NCH];
+          int ec[NCH];
+          BinEval v[NCH];
+          float d[NCH];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            const int idx = id0 + lane + ((c * 32 + lane < rem) ? c * 32 : 0);   // lane < 32 < rem
+            ev[c] = qv[idx];
+            ec[c] = (int)qc[idx];
+          }
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) v[c] = dense_eval<EPI, LOGD>(prm, bnd, ev[c], ec[c], d[c]);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (c * 32 + lane < rem) {
+              nll_part -= v[c].logp;
+              qv[id0 + lane + c * 32] = v[c].gx * d[c];
+            }
+          }
         }
         __syncwarp();
         w = base;
@@ -510,18 +583,24 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
         for (int i = 0; i < DT_SLAB; ++i) {
           const uint32_t code = (cw[i >> 2] >> (8 * (i & 3))) & 0xffu;
           float g = 0.0f;
-          if (code != 255u) g = __uint_as_float(q[w++].x);
+          if (code != 255u) g = qv[w++];
           x[i] = g;
         }
       }
       if (GRAD) {
         if (blk > 0) {
-          // the previous block's gradient MMAs must have consumed the G buffers before they are overwritten
+          // the previous block's MMA2 must have consumed the G buffer before it is overwritten,
           dmbar_wait(&bar2, ph2);
           ph2 ^= 1;
         }
+        if (blk > 1) {
+          // and MMA3 of the block before that this block's G^T buffer
+          dmbar_wait(&bar3[blk & 1], ph3[blk & 1]);
+          ph3[blk & 1] ^= 1;
+        }
+        const uint32_t gth = map.gt + (uint32_t)(blk & 1) * 2 * GT_BYTES, gtl = gth + GT_BYTES;
 #pragma unroll
-        for (int c4 = 0; c4 < DT_SLAB / 4; ++c4) {
+        for (int c4 = 0; c4 < ((prm.debug & 8) ? 0 : DT_SLAB / 4); ++c4) {
           const float4 h4 = make_float4(tf32_hi(x[4 * c4]), tf32_hi(x[4 * c4 + 1]), tf32_hi(x[4 * c4 + 2]), tf32_hi(x[4 * c4 + 3]));
           const float4 l4 = make_float4(x[4 * c4] - h4.x, x[4 * c4 + 1] - h4.y, x[4 * c4 + 2] - h4.z, x[4 * c4 + 3] - h4.w);
           const uint32_t o = (uint32_t)(half * (DT_SLAB / 4) + c4) * 2048 + row * 16;
@@ -529,14 +608,14 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
           *reinterpret_cast<float4*>(dsm + map.gl + o) = l4;
           // transposed copy: element (band, pixel) at chunk pixel/4, row band, word pixel%4
           const uint32_t ot = (uint32_t)(row >> 2) * GT_PITCH + (uint32_t)(half * DT_SLAB + 4 * c4) * 16 + (row & 3) * 4;
-          *reinterpret_cast<float*>(dsm + map.gth + ot) = h4.x;
-          *reinterpret_cast<float*>(dsm + map.gth + ot + 16) = h4.y;
-          *reinterpret_cast<float*>(dsm + map.gth + ot + 32) = h4.z;
-          *reinterpret_cast<float*>(dsm + map.gth + ot + 48) = h4.w;
-          *reinterpret_cast<float*>(dsm + map.gtl + ot) = l4.x;
-          *reinterpret_cast<float*>(dsm + map.gtl + ot + 16) = l4.y;
-          *reinterpret_cast<float*>(dsm + map.gtl + ot + 32) = l4.z;
-          *reinterpret_cast<float*>(dsm + map.gtl + ot + 48) = l4.w;
+          *reinterpret_cast<float*>(dsm + gth + ot) = h4.x;
+          *reinterpret_cast<float*>(dsm + gth + ot + 16) = h4.y;
+          *reinterpret_cast<float*>(dsm + gth + ot + 32) = h4.z;
+          *reinterpret_cast<float*>(dsm + gth + ot + 48) = h4.w;
+          *reinterpret_cast<float*>(dsm + gtl + ot) = l4.x;
+          *reinterpret_cast<float*>(dsm + gtl + ot + 16) = l4.y;
+          *reinterpret_cast<float*>(dsm + gtl + ot + 32) = l4.z;
+          *reinterpret_cast<float*>(dsm + gtl + ot + 48) = l4.w;
         }
         fence_async();       // generic-proxy writes of G -> visible to the tensor core's async proxy
         tc_fence_before();
@@ -547,8 +626,17 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
     d3_started = true;
     if (GRAD && !issuer) {
       // ---- gS tile out of D2 ---------------------------------------------------------------------
-      dmbar_wait(&bar2, ph2);
+      dmbar_wait(&bar2, ph2);   // the last block's MMA2: D2 is complete
       ph2 ^= 1;
+      // every MMA3 still in flight (the last one or two blocks'): the next tile re-stages their S operand, and D3 is
+      // read after the last tile
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (i < nblk) {
+          dmbar_wait(&bar3[i], ph3[i]);
+          ph3[i] ^= 1;
+        }
+      }
       tc_fence_after();
       if (half == 0) {
         float v[16];
@@ -639,10 +727,12 @@ template <int EPI>
 static int dense_launch(const DenseParams& prm, bool logd, bool grad, int grid, size_t smem, cudaStream_t st) {
 #define QMC_DENSE_GO(L, G)                                                                                   \
   do {                                                                                                       \
-    auto kern = dense_kernel<EPI, L, G>;                                                                     \
+    auto kern = dense_kernel<EPI, L, G, QMC_DENSE_NCH>;                                                      \
+    if (nch_alt) kern = dense_kernel<EPI, L, G, QMC_DENSE_NCH_ALT>;                                          \
     QMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     kern<<<grid, DT_LAUNCH, smem, st>>>(prm);                                                               \
   } while (0)
+  static const bool nch_alt = getenv("QMC_DENSE_NCH_ALT") != nullptr;   // measurement hook
   if (logd) { if (grad) QMC_DENSE_GO(true, true); else QMC_DENSE_GO(true, false); }
   else { if (grad) QMC_DENSE_GO(false, true); else QMC_DENSE_GO(false, false); }
 #undef QMC_DENSE_GO
@@ -727,6 +817,10 @@ static int dense_entry(const float* S_dev, const float* C_dev, const uint8_t* co
               : (lik->flags & QMC_EPI_LOGISTIC) ? 1.0f / lik->noise_std      // logistic scale, no sqrt(2)
                                                 : 1.0f / probit_scale(lik->noise_std);
   prm.one_sided = 0;
+  {
+    const char* e = getenv("QMC_DENSE_DEBUG");
+    prm.debug = e ? atoi(e) : 0;
+  }
   prm.offset = lik->offset;
   for (int i = 0; i < lik->n_bounds; ++i) prm.bounds[i] = lik->bounds[i];
   prm.thr = lik->n_bounds >= 3 ? lik->bounds[1] : 0.0f;

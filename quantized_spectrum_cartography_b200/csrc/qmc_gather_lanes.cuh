@@ -163,11 +163,27 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   // the first copies need not know its length.
   const uint32_t hdr_a = smem_u32(smem + L.hdr) + (uint32_t)(warp * prm.n_runs * 32 + lane) * 4u;
   const uint32_t ring_a = smem_u32(smem + L.ring) + (uint32_t)((warp * SLOTS) * 32 + lane) * 16u;
-  if (!bulk) {
-    // emitter-major storage (the reference's [R][IJ]): the slice is transposed into [p][r] rows by 4-byte
-    // asynchronous copies, all in flight at once and in a cp.async group of their own, older than the ring's.  RP
-    // consecutive lanes take the RP emitters of one pixel: the shared-memory side of a copy is 32 consecutive
-    // words (no bank conflict), the global side RP runs of 32/RP consecutive pixels.
+  // emitter-major storage with contiguous pixels (the reference's [R][IJ]; rows are not 16-byte aligned at IJ = 2601, so
+  // no bulk copy): lane = pixel.  Each lane loads the R emitters of its pixels with coalesced 4-byte loads (one
+  // 128-byte run per emitter and instruction), NU pixels per lane in flight at once, and stores whole [p][r] rows
+  // with one 16-byte shared-memory store each -- a transposition through registers, ~5 instructions per pixel row
+  // instead of ~15 for element-wise copies.  The loads are issued here, with the other loads of the prologue; the
+  // stores follow further down, once everything else is on its way.
+  constexpr int NU = RP <= 4 ? 11 : RP == 8 ? 5 : 2;   // pixels per lane in flight (registers: NU * RP)
+  const bool em_rows = !bulk && prm.sP == 1 && (RP % 4) == 0;
+  float emv[(RP % 4) == 0 ? NU : 1][RP];
+  if (em_rows) {
+    const float* src = Sb + (int64_t)(p0 + sl0) + lane;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+#pragma unroll
+      for (int r = 0; r < RP; ++r)
+        emv[u][r] = (u * 32 + lane < sln && r < prm.R) ? __ldg(src + (int64_t)r * prm.sR + u * 32) : 0.0f;
+    }
+  } else if (!bulk) {
+    // any other strides: the slice is transposed into [p][r] rows by 4-byte asynchronous copies, all in flight at
+    // once and in a cp.async group of their own, older than the ring's.  RP consecutive lanes take the RP emitters
+    // of one pixel: the shared-memory side of a copy is 32 consecutive words (no bank conflict).
     constexpr int PPI = RP <= 32 ? 32 / RP : 1;  // pixels per copy instruction
     const int r = lane % RP, pq = lane / RP;
     const uint32_t Sw_a = smem_u32(Sw);
@@ -227,6 +243,38 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       prefetch_l2(v2 + o);
     }
   }
+  if (em_rows) {
+    if constexpr ((RP % 4) == 0) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int pl = u * 32 + lane;
+        if (pl < sln) {
+#pragma unroll
+          for (int r = 0; r < RP; r += 4)
+            *reinterpret_cast<float4*>(Sw + pl * RP + r) = make_float4(emv[u][r], emv[u][r + 1], emv[u][r + 2], emv[u][r + 3]);
+        }
+      }
+      // slices longer than 32 * NU pixels: the rest in further rounds (each one a memory round trip)
+      for (int base = 32 * NU; base < sln; base += 32 * NU) {
+        const float* src = Sb + (int64_t)(p0 + sl0) + base + lane;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+#pragma unroll
+          for (int r = 0; r < RP; ++r)
+            emv[u][r] = (base + u * 32 + lane < sln && r < prm.R) ? __ldg(src + (int64_t)r * prm.sR + u * 32) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          const int pl = base + u * 32 + lane;
+          if (pl < sln) {
+#pragma unroll
+            for (int r = 0; r < RP; r += 4)
+              *reinterpret_cast<float4*>(Sw + pl * RP + r) = make_float4(emv[u][r], emv[u][r + 1], emv[u][r + 2], emv[u][r + 3]);
+          }
+        }
+      }
+    }
+  }
   if (GRAD) {
     float* zc = gCw + (size_t)warp * (K + XROWS) * RP;
     if (RP % 4 == 0) {
@@ -251,7 +299,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   const int ngroups = nrows_v >> 2;
   __syncthreads();  // Csm and `done` are ready; the slices are private to their warps
   if (use_bar) mbar_wait(&mbar[warp], 0);
-  if (!bulk) cp_async_wait<SLOTS>();  // the S slice (every group but the ring's SLOTS newest)
+  if (!bulk && !em_rows) cp_async_wait<SLOTS>();  // the S slice (every group but the ring's SLOTS newest)
   __syncwarp();
 
   constexpr uint32_t ROWB = RP * sizeof(float);
@@ -575,16 +623,31 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       __syncwarp();
       if (lane == 0) bulk_s2g(gSb + (int64_t)(p0 + sl0) * RP, gSw, (uint32_t)sln * RP * sizeof(float));
     } else {
-      // emitter-major: RP consecutive lanes take the RP emitters of one pixel -- conflict-free 4-byte reads of
-      // the tile, R runs of consecutive pixels per store instruction
       __syncwarp();
-      constexpr int PPI = RP <= 32 ? 32 / RP : 1;
-      const int r = lane % RP, pq = lane / RP;
-      if (r < prm.R) {
-        float* dst = gSb + (int64_t)r * prm.sR + (int64_t)(p0 + sl0 + pq) * prm.sP;
-        const int64_t dstep = (int64_t)PPI * prm.sP;
-        const float* srcp = gSw + pq * RP + r;
-        for (int pl = pq; pl < sln; pl += PPI, dst += dstep, srcp += PPI * RP) *dst = *srcp;
+      if (prm.sP == 1 && (RP % 4) == 0) {
+        // emitter-major rows: lane = pixel, one 16-byte read of the tile row per 4 emitters, R coalesced 4-byte stores
+        float* dst = gSb + (int64_t)(p0 + sl0);
+        for (int pl = lane; pl < sln; pl += 32) {
+#pragma unroll
+          for (int r = 0; r < RP; r += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(gSw + pl * RP + r);
+            if (r < prm.R) __stcg(dst + (int64_t)r * prm.sR + pl, v.x);
+            if (r + 1 < prm.R) __stcg(dst + (int64_t)(r + 1) * prm.sR + pl, v.y);
+            if (r + 2 < prm.R) __stcg(dst + (int64_t)(r + 2) * prm.sR + pl, v.z);
+            if (r + 3 < prm.R) __stcg(dst + (int64_t)(r + 3) * prm.sR + pl, v.w);
+          }
+        }
+      } else {
+        // any other strides: RP consecutive lanes take the RP emitters of one pixel -- conflict-free 4-byte reads
+        // of the tile
+        constexpr int PPI = RP <= 32 ? 32 / RP : 1;
+        const int r = lane % RP, pq = lane / RP;
+        if (r < prm.R) {
+          float* dst = gSb + (int64_t)r * prm.sR + (int64_t)(p0 + sl0 + pq) * prm.sP;
+          const int64_t dstep = (int64_t)PPI * prm.sP;
+          const float* srcp = gSw + pq * RP + r;
+          for (int pl = pq; pl < sln; pl += PPI, dst += dstep, srcp += PPI * RP) *dst = *srcp;
+        }
       }
     }
   }
