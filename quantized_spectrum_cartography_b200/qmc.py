@@ -192,7 +192,7 @@ def solve_lowrank_fused(S0: torch.Tensor, C0: torch.Tensor, obs, lik, cfg: Solve
     ssS, ssS_next = (torch.empty(B, dtype=torch.float64, device=dev) for _ in range(2))   # ||S_b||_F^2
     ssC, ssC_next = (torch.empty(B, dtype=torch.float64, device=dev) for _ in range(2))
     view = obs.view()
-    fused_s = bool(fuse_s_step and obs.lanes and R % 4 == 0 and obs.n_sub == obs.tile_warps and not lik.flags & _lib.QMC_FORWARD_ONLY
+    fused_s = bool(fuse_s_step and obs.lanes and R in (4, 8, 16, 32) and obs.n_sub == obs.tile_warps and not lik.flags & _lib.QMC_FORWARD_ONLY
                    and S.stride(1) == 1 and S.stride(2) == R)
     ctr = torch.zeros(2, dtype=torch.int32, device=dev)          # Adam steps taken on C, on S
     ctr_c, ctr_s = ctr.data_ptr(), ctr.data_ptr() + 4

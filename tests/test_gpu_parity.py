@@ -847,13 +847,14 @@ def test_cuda_graph_solver_matches_eager(q):
         np.testing.assert_allclose(nb.cpu().numpy(), na.cpu().numpy(), rtol=1e-4)
 
 
-@pytest.mark.parametrize("K,tiled,pixel_major,graph", [(16, True, False, False), (64, True, True, False),
-                                                       (64, True, True, True), (16, False, False, False)])
-def test_fused_solver_matches_torch_solver(q, K, tiled, pixel_major, graph):
+@pytest.mark.parametrize("K,tiled,pixel_major,graph,R", [(16, True, False, False, 4), (64, True, True, False, 4),
+                                                         (64, True, True, True, 4), (16, False, False, False, 4),
+                                                         (64, True, True, False, 12)])   # 12: padded rank 16 != R, no fused S-step
+def test_fused_solver_matches_torch_solver(q, K, tiled, pixel_major, graph, R):
     """The autograd-free solver (fused evaluation + qmc_adam_frob_project) walks the same trajectory as
     autograd + torch.optim.Adam + torch.norm + clamp_ on the same start point."""
     from quantized_spectrum_cartography_b200 import qmc
-    B, I, J, R = 5, 20, 21, 4
+    B, I, J = 5, 20, 21
     S, C, Y, Wx, bb, sigma, off = _random_instance(B, I, J, K, R, 0.3, 2, seed=78)
     lik = q.make_likelihood(bb, sigma)
     obs = q.make_obs(Y.cuda(), Wx.cuda(), K, "cuda", B=B, R=R, tiled=tiled, tile_warps=4)
