@@ -49,6 +49,8 @@ struct DenseParams {
   float* gS;             // [R][IJ], row stride gs_stride
   int64_t gs_stride;
   float* gC;             // [R][K]
+  float* gC_acc;         // where the CTAs add their partial gC and NLL: the outputs themselves (zeroed by the host), or,
+  double* nll_acc;       // with the fused exchange, the self-cleaning scratch slot of this rank's exchange region
   int IJ, K, R, Rp8, n_tiles;
   int tile_pix;          // pixels a tile really holds (<= DT_PIX; the rest of the 128 TMEM lanes idles), chosen by the host so
                          // that the tiles divide evenly over the persistent CTAs
@@ -64,7 +66,9 @@ struct DenseParams {
 // ---- exchange region (one per rank, device memory mapped into every peer through CUDA IPC) -------------------------
 //   [0, 256)  header: epoch (exchanges completed), status (0 = fine, 1 = a peer never arrived), done (CTA counter)
 //             and, from byte 128, flag[q] = the last epoch rank q has delivered into this region
-//   then two sets (epoch parity) of `world` slots of slot_floats floats: slot q = rank q's partial [gC | nll as a double]
+//   then a scratch slot the CTAs of a launch add their partials into (the last CTA reads it and leaves it zeroed for
+//   the next launch: no memset nodes around the kernel), then
+//   two sets (epoch parity) of `world` slots of slot_floats floats: slot q = rank q's partial [gC | nll as a double]
 // A rank can run at most one exchange ahead of a peer (it needs the peer's flag of epoch e to finish e, and the peer
 // raises it only after it has read everything of epoch e-1), hence two slot sets and a monotonic flag are enough.
 struct PeerHeader {
@@ -73,7 +77,7 @@ struct PeerHeader {
 };
 static_assert(sizeof(PeerHeader) == 256, "PeerHeader is the first 256 bytes of a region");
 __host__ __device__ inline size_t peer_slot_offset(int world, int slot_floats, int parity, int q) {
-  return sizeof(PeerHeader) + ((size_t)parity * world + q) * (size_t)slot_floats * 4;
+  return sizeof(PeerHeader) + (1 + (size_t)parity * world + q) * (size_t)slot_floats * 4;   // slot 0 is the scratch
 }
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -103,12 +107,31 @@ __device__ void peer_exchange(const DenseParams& prm, int nthreads) {
   PeerHeader* own = reinterpret_cast<PeerHeader*>(prm.px_region[rank]);
   const uint32_t e = own->epoch + 1;                   // written only by this code path, one kernel at a time
   const int par = (int)(e & 1u);
-  const float4* part = reinterpret_cast<const float4*>(prm.gC);
-  const double nll_part = __ldcg(prm.nll);
+  // this rank's partial sums: out of the scratch slot into registers, and the scratch slot back to zero
+  constexpr int PV = 4;                                // float4 per thread: R*K <= 16*256 floats = 1024 float4 <= 4 * 512
+  float4* part = reinterpret_cast<float4*>(prm.gC_acc);
+  float4 pv[PV];
+#pragma unroll
+  for (int u = 0; u < PV; ++u) {
+    const int i = tid + u * nthreads;
+    if (i < n4) {
+      pv[u] = __ldcg(part + i);
+      __stcg(part + i, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+  double nll_part = 0.0;
+  if (tid == 0) {
+    nll_part = __ldcg(prm.nll_acc);
+    __stcg(prm.nll_acc, 0.0);
+  }
   for (int q0 = 0; q0 < world; ++q0) {
     const int q = (rank + 1 + q0) % world;             // start with the neighbour: the ranks do not all hit rank 0 first
     float4* dst = reinterpret_cast<float4*>(prm.px_region[q] + peer_slot_offset(world, prm.px_slot_floats, par, rank));
-    for (int i = tid; i < n4; i += nthreads) dst[i] = __ldcg(part + i);
+#pragma unroll
+    for (int u = 0; u < PV; ++u) {
+      const int i = tid + u * nthreads;
+      if (i < n4) dst[i] = pv[u];
+    }
     if (tid == 0) *reinterpret_cast<double*>(dst + n4) = nll_part;
   }
   __threadfence_system();
@@ -126,8 +149,13 @@ __device__ void peer_exchange(const DenseParams& prm, int nthreads) {
     }
   }
   __syncthreads();
-  if (px_failed) {
-    if (tid == 0) { own->status = 1; own->done = 0; own->epoch = e; }
+  if (px_failed) {   // a peer never arrived: flag it and hand back this rank's own partial sums
+#pragma unroll
+    for (int u = 0; u < PV; ++u) {
+      const int i = tid + u * nthreads;
+      if (i < n4) reinterpret_cast<float4*>(prm.gC)[i] = pv[u];
+    }
+    if (tid == 0) { *prm.nll = nll_part; own->status = 1; own->done = 0; own->epoch = e; }
     return;
   }
   const uint8_t* slots = prm.px_region[rank] + peer_slot_offset(world, prm.px_slot_floats, par, 0);
@@ -668,7 +696,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
         if (lane < 16) {
 #pragma unroll
           for (int r = 0; r < 16; ++r)
-            if (r < R) atomicAdd(prm.gC + (size_t)r * K + band, v[r]);
+            if (r < R) atomicAdd(prm.gC_acc + (size_t)r * K + band, v[r]);
         }
       }
     }
@@ -680,7 +708,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
   if (tid == 0) {
     double tot = 0.0;
     for (int i = 0; i < DT_LAUNCH / 32; ++i) tot += wsum[i];
-    if (tot != 0.0) atomicAdd(prm.nll, tot);
+    if (tot != 0.0) atomicAdd(prm.nll_acc, tot);
   }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
@@ -797,6 +825,13 @@ static int dense_entry(const float* S_dev, const float* C_dev, const uint8_t* co
     }
     prm.px_rank = px->rank; prm.px_world = px->world; prm.px_slot_floats = px->slot_floats;
   }
+  prm.gC_acc = gC_out_dev;
+  prm.nll_acc = nll_out_dev;
+  if (px) {
+    float* scratch = reinterpret_cast<float*>((uint8_t*)px->region[px->rank] + sizeof(PeerHeader));
+    prm.gC_acc = scratch;
+    prm.nll_acc = reinterpret_cast<double*>(scratch + R * K);   // R*K is a multiple of 32: 8-byte aligned
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -839,8 +874,10 @@ static int dense_entry(const float* S_dev, const float* C_dev, const uint8_t* co
   }
   const bool logd = (lik->flags & QMC_LOG_DOMAIN) != 0;
 
-  QMC_CUDA_CHECK(cudaMemsetAsync(nll_out_dev, 0, sizeof(double), st));
-  if (grad) QMC_CUDA_CHECK(cudaMemsetAsync(gC_out_dev, 0, sizeof(float) * (size_t)R * K, st));
+  if (!px) {   // (with the exchange the partials go through the region's scratch slot, which the kernel leaves zeroed)
+    QMC_CUDA_CHECK(cudaMemsetAsync(nll_out_dev, 0, sizeof(double), st));
+    if (grad) QMC_CUDA_CHECK(cudaMemsetAsync(gC_out_dev, 0, sizeof(float) * (size_t)R * K, st));
+  }
   const size_t smem = dense_smem_map(K, prm.Rp8).total;
   const int grid = prm.n_tiles < sms ? prm.n_tiles : sms;
   switch (epi) {

@@ -219,8 +219,8 @@ class ShardedInstance:
                 buf[: R * n].view(R, n).copy_(gSl.reshape(R, -1))
             gC_view.copy_(gC.reshape(R, K))
             self._nll64.copy_(nll.reshape(1).to(torch.float64))
-        if self._peers is not None:
-            return                           # the kernel left the global sums in place: nothing travels through `tail`
+        if self._peers is not None or _world()[1] == 1:
+            return                           # the global sums are in place already: nothing travels through `tail`
         hi32 = self._nll64.to(torch.float32)
         tail[0:1].copy_(hi32)
         tail[1:2].copy_((self._nll64 - hi32.to(torch.float64)).to(torch.float32))
@@ -286,7 +286,7 @@ class ShardedInstance:
         buf = self._buf
         off = R * IJ if self.mode == "flat" else R * n
         gC_all = buf[off: off + R * K].view(R, K)
-        if self._peers is not None:
+        if self._peers is not None or world == 1:
             nll = self._nll64[0].clone()
         else:
             nll = buf[off + R * K].to(torch.float64) + buf[off + R * K + 1].to(torch.float64)
