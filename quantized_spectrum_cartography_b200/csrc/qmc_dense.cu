@@ -161,11 +161,16 @@ __device__ void peer_exchange(const DenseParams& prm, int nthreads) {
   const uint8_t* slots = prm.px_region[rank] + peer_slot_offset(world, prm.px_slot_floats, par, 0);
   const size_t pitch = (size_t)prm.px_slot_floats * 4;
   for (int i = tid; i < n4; i += nthreads) {
-    float4 a = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(slots) + i);
-    for (int q = 1; q < world; ++q) {
-      const float4 b = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(slots + q * pitch) + i);
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-    }
+    // all the slots' loads in flight at once (a load from a region the peers write is an L2 round trip), then the sum
+    // in rank order
+    float4 v[QMC_PEER_MAX_WORLD];
+#pragma unroll
+    for (int q = 0; q < QMC_PEER_MAX_WORLD; ++q)
+      if (q < world) v[q] = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(slots + q * pitch) + i);
+    float4 a = v[0];
+#pragma unroll
+    for (int q = 1; q < QMC_PEER_MAX_WORLD; ++q)
+      if (q < world) { a.x += v[q].x; a.y += v[q].y; a.z += v[q].z; a.w += v[q].w; }
     reinterpret_cast<float4*>(prm.gC)[i] = a;
   }
   if (tid == 0) {
@@ -268,6 +273,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 // The same load in two halves: issue (the registers are written asynchronously) and wait (the registers pass through
 // the wait as read-write operands, so nothing that uses them can be scheduled above it)
 __device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
@@ -554,23 +567,24 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
         int cnt = 0;
 #pragma unroll
         for (int i = 0; i < DT_SLAB; ++i) cnt += ((cw[i >> 2] >> (8 * (i & 3))) & 0xffu) != 255u;
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const int base = incl - cnt;
+        // exclusive prefix sum of the counts (0..DT_SLAB = 8: four bits) out of four ballots -- a shuffle scan compiles
+        // into five calls of an out-of-line collective routine here (~140 instructions per block)
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1), b1 = __ballot_sync(0xffffffffu, cnt & 2);
+        const uint32_t b2 = __ballot_sync(0xffffffffu, cnt & 4), b3 = __ballot_sync(0xffffffffu, cnt & 8);
+        const int base = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
+        const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
         float* qv = reinterpret_cast<float*>(dsm + map.queue + warp * QUEUE_WARP_BYTES);
         uint8_t* qc = reinterpret_cast<uint8_t*>(qv + 32 * DT_SLAB);
-        int w = base;
+        {
+          int w = base;
 #pragma unroll
-        for (int i = 0; i < DT_SLAB; ++i) {
-          const uint32_t code = (cw[i >> 2] >> (8 * (i & 3))) & 0xffu;
-          if (code != 255u) {
-            qv[w] = x[i];
-            qc[w++] = (uint8_t)code;
+          for (int i = 0; i < DT_SLAB; ++i) {
+            const uint32_t code = (cw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            if (code != 255u) {
+              qv[w] = x[i];
+              qc[w++] = (uint8_t)code;
+            }
           }
         }
         __syncwarp();
@@ -606,7 +620,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
           }
         }
         __syncwarp();
-        w = base;
+        int w = base;
 #pragma unroll
         for (int i = 0; i < DT_SLAB; ++i) {
           const uint32_t code = (cw[i >> 2] >> (8 * (i & 3))) & 0xffu;
@@ -666,13 +680,15 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
         }
       }
       tc_fence_after();
-      if (half == 0) {
-        float v[16];
-        tmem_ld16(tlane + COL_D2, v);
+      {   // the four warps of a lane quadrant take four ranks each
+        float v[4];
+        tmem_ld4(tlane + COL_D2 + (uint32_t)(half * 4), v);
         if (inside) {
 #pragma unroll
-          for (int r = 0; r < 16; ++r)
-            if (r < R) prm.gS[(size_t)r * prm.gs_stride + p0 + pix] = v[r];
+          for (int i = 0; i < 4; ++i) {
+            const int r = half * 4 + i;
+            if (r < R) prm.gS[(size_t)r * prm.gs_stride + p0 + pix] = v[i];
+          }
         }
       }
     }
