@@ -6,7 +6,7 @@
  * Every function returns 0 on success and a QMC_ERR_* code otherwise; qmc_last_error() gives the
  * message for the calling thread.  All `*_dev` pointers are device pointers on the current CUDA
  * device, `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  The library
- * never allocates device memory: the caller owns every buffer.  Its process-wide state is the thread-local error
+ * never allocates device memory (except qmc_peer_alloc, whose job it is): the caller owns every buffer.  Its process-wide state is the thread-local error
  * string, the launch counter, and -- for qmc_nll_fwd_bwd_gather_host only -- one lazily created set of internal
  * copy/compute streams per device, guarded by a per-device mutex (calls on one device are serialised, different
  * devices proceed independently).  There is no CPU implementation behind these entry points.
@@ -256,6 +256,9 @@ QMC_API int64_t qmc_dense_smem_bytes(int K, int R);
  * evaluates its pixel block, and the kernel's last CTA writes the rank's partial [gC | nll] into a slot of every
  * peer's exchange region (plain stores through NVLink peer mappings), publishes a flag, waits for the peers' flags
  * and adds the slots up in rank order -- every rank ends with the same bits, no NCCL call, no second launch.
+ *
+ * The partial sums of a launch's CTAs go through a scratch slot of the rank's own region that the kernel leaves
+ * zeroed, so the call is one kernel launch and nothing else (no memset of the outputs).
  *
  * An exchange region is device memory of qmc_peer_region_bytes() bytes allocated by qmc_peer_alloc (which also
  * returns the 64-byte CUDA IPC handle the other ranks open with qmc_peer_open; exchange the handles with any host

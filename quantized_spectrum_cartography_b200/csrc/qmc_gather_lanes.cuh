@@ -556,8 +556,18 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       const bool turn = todo && (__ffs(m) - 1) == lane;
       if (turn) {
         const uint32_t dst = gC_a + band0 * ROWB, src = gC_a + row0 * ROWB;
+        if (RP % 4 == 0) {
 #pragma unroll
-        for (int r = 0; r < RP; ++r) sts32(dst + r * 4, lds32(dst + r * 4) + lds32(src + r * 4));
+          for (int r = 0; r < RP; r += 4) {
+            float4 d = lds128(dst + r * 4);
+            const float4 e = lds128(src + r * 4);
+            d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
+            sts128(dst + r * 4, d);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < RP; ++r) sts32(dst + r * 4, lds32(dst + r * 4) + lds32(src + r * 4));
+        }
       }
       todo = todo && !turn;
       __syncwarp();

@@ -47,7 +47,7 @@ def main():
                     c[k] += 1
     print(f"\n# gather_lanes_kernel<4, ONEBIT, linear, both gradients, 16-bit words>: {n} SASS instructions")
     print("  " + ", ".join(f"{k} {c[k]}" for k in MARK if c[k]))
-    out = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3qmc12dense_kernelILi0ELb1ELb1EEEvNS_11DenseParamsE",
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3qmc12dense_kernelILi0ELb1ELb1ELi4EEEvNS_11DenseParamsE",
                           os.path.join(ROOT, "quantized_spectrum_cartography_b200", "build", "qmc_dense.o")], capture_output=True, text=True).stdout
     c = collections.Counter()
     n = 0
@@ -58,7 +58,7 @@ def main():
             for k in MARK:
                 if m.group(1).startswith(k):
                     c[k] += 1
-    print(f"\n# dense_kernel<STABLE, log domain, gradients> (cfg4): {n} SASS instructions")
+    print(f"\n# dense_kernel<STABLE, log domain, gradients, 4 evaluations in flight> (cfg4): {n} SASS instructions")
     print("  " + ", ".join(f"{k} {c[k]}" for k in MARK if c[k]))
 
 
