@@ -665,7 +665,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if em_ms is not None:
         roofline_em = {"bound": "hbm", "achieved": alg_bytes / (em_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                        "frac": alg_bytes / (em_ms * 1e-3) / 1e9 / peak, "mean_launch_ms": em_ms,
-                       "S_layout": "emitter_major (the reference's [R,1,I,J]; transposed into shared-memory rows by 4-byte asynchronous copies)"}
+                       "S_layout": "emitter_major (the reference's [R,1,I,J]; slices transposed through registers: coalesced row loads, 16-byte shared-memory stores)"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only

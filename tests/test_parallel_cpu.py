@@ -110,3 +110,20 @@ def test_sharded_and_batched_paths_world_size_2(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_fused_exchange_is_refused_where_it_cannot_run():
+    """exchange="peer" is part of the dense tcgen05 kernel: it carries [gC | nll] only (pixel_block mode) and needs the
+    CUDA evaluator on a dense observation set; anything else is refused when the instance is built, not at run time."""
+    Y = torch.zeros(8, 12, dtype=torch.int64)
+    Wx = torch.ones(8, 12)
+    lik = object()
+    with pytest.raises(ValueError, match="carries"):
+        par.ShardedInstance.from_dense(Y, Wx, 8, 2, lik, mode="flat", exchange="peer")
+    with pytest.raises(ValueError, match="exchange"):
+        par.ShardedInstance.from_dense(Y, Wx, 8, 2, lik, mode="pixel_block", exchange="nvshmem")
+    with pytest.raises(ValueError, match="dense tcgen05"):   # an injected evaluator / a non-dense observation set
+        par.ShardedInstance.from_dense(Y, Wx, 8, 2, lik, mode="pixel_block", exchange="peer", build=lambda y, w: (y, w),
+                                       local_eval=lambda *a, **k: None)
+    assert par.ShardedInstance.from_dense(Y, Wx, 8, 2, lik, mode="pixel_block", build=lambda y, w: (y, w),
+                                          local_eval=lambda *a, **k: None).exchange_status() == 0
