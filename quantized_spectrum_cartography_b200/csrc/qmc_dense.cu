@@ -443,6 +443,66 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
   const int nblk = K / DT_BLK;
   const bool short_tile = prm.tile_pix < DT_PIX;
 
+  // ---- staging of a tile's S rows: A1 (MMA1) and B3h/B3l (MMA3); threads 0..255: operand row p (= TMEM lane), 8 ranks
+  // each.  A tile's rows are loaded and its A1 written while the previous tile's last MMAs drain (A1 is free as soon
+  // as MMA1 has run); B3 follows once those MMAs are done.
+  float st_h[8], st_l[8];
+  auto stage_load_a1 = [&](int t) {
+    if (tid < 256) {
+      const int p = tid & 127, rh = tid >> 7;
+      const int ppix = short_tile ? ((p & 31) << 2 | (p >> 5)) : p;
+      const int pg = t * prm.tile_pix + ppix;
+      const bool in = ppix < prm.tile_pix && pg < prm.IJ;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rh * 8 + i;
+        const float sv = (in && r < R) ? __ldg(prm.S + (size_t)r * prm.IJ + pg) : 0.0f;
+        st_h[i] = tf32_hi(sv);
+        st_l[i] = sv - st_h[i];
+      }
+      if (rh * 8 < Rp8) {   // A1 row = pixel p, elements [Sh | Sl]
+        const int per = Rp8 / 4;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int jr = rh * 2 + q;   // chunk index inside one Rp8-wide segment
+          *reinterpret_cast<float4*>(dsm + map.a1 + (size_t)(jr) * 2048 + p * 16) =
+              make_float4(st_h[4 * q], st_h[4 * q + 1], st_h[4 * q + 2], st_h[4 * q + 3]);
+          *reinterpret_cast<float4*>(dsm + map.a1 + (size_t)(per + jr) * 2048 + p * 16) =
+              make_float4(st_l[4 * q], st_l[4 * q + 1], st_l[4 * q + 2], st_l[4 * q + 3]);
+        }
+      }
+    }
+  };
+  auto stage_b3 = [&]() {
+    if (GRAD && tid < 256) {
+      const int p = tid & 127, rh = tid >> 7;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rh * 8 + i;
+        const uint32_t o = (p >> 2) * 256 + (r >> 3) * 128 + (r & 7) * 16 + (p & 3) * 4;
+        *reinterpret_cast<float*>(dsm + map.b3h + o) = st_h[i];
+        *reinterpret_cast<float*>(dsm + map.b3l + o) = st_l[i];
+      }
+    }
+  };
+  // code bytes of a tile's first block for this thread's row (fetched with the staging, a tile ahead)
+  auto first_codes = [&](int t) -> uint2 {
+    const int pixl = short_tile ? ((row & 31) << 2 | (row >> 5)) : row;
+    const int pg = t * prm.tile_pix + pixl;
+    uint2 c = make_uint2(0xffffffffu, 0xffffffffu);
+    if (!issuer && t < prm.n_tiles && pixl < prm.tile_pix && pg < prm.IJ)
+      c = __ldg(reinterpret_cast<const uint2*>(prm.code + (size_t)pg * K + half * DT_SLAB));
+    return c;
+  };
+  uint2 cfirst = first_codes(blockIdx.x);
+  if (blockIdx.x < prm.n_tiles) {
+    stage_load_a1(blockIdx.x);
+    stage_b3();
+  }
+  fence_async();
+  tc_fence_before();
+  __syncthreads();
+
   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
     const int p0 = tile * prm.tile_pix;
     // the code bytes of a block are fetched one block ahead (the first block's here, before the tile is staged):
@@ -452,42 +512,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
     const int pix = short_tile ? ((row & 31) << 2 | (row >> 5)) : row;
     const bool inside = pix < prm.tile_pix && p0 + pix < prm.IJ;
     const uint8_t* crow = prm.code + (size_t)(p0 + pix) * K;
-    uint2 cnext = make_uint2(0xffffffffu, 0xffffffffu);
-    if (inside && !issuer) cnext = __ldg(reinterpret_cast<const uint2*>(crow + half * DT_SLAB));
-    // ---- stage the S tile: A1 (MMA1) and B3h/B3l (MMA3) -------------------------------------------
-    if (tid < 256) {
-      const int p = tid & 127, rh = tid >> 7;   // operand row (= TMEM lane), rank half (8 ranks each)
-      const int ppix = short_tile ? ((p & 31) << 2 | (p >> 5)) : p;
-      const bool inside = ppix < prm.tile_pix && p0 + ppix < prm.IJ;
-      float sh[8], sl[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rh * 8 + i;
-        const float s = (inside && r < R) ? __ldg(prm.S + (size_t)r * prm.IJ + p0 + ppix) : 0.0f;
-        sh[i] = tf32_hi(s);
-        sl[i] = s - sh[i];
-        const uint32_t o = (p >> 2) * 256 + (r >> 3) * 128 + (r & 7) * 16 + (p & 3) * 4;
-        if (GRAD) {
-          *reinterpret_cast<float*>(dsm + map.b3h + o) = sh[i];
-          *reinterpret_cast<float*>(dsm + map.b3l + o) = sl[i];
-        }
-      }
-      // A1 row = pixel p, elements [Sh | Sl]; this thread owns ranks rh*8 .. rh*8+7 (if < Rp8)
-      if (rh * 8 < Rp8) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int jr = rh * 2 + q;   // chunk index inside one Rp8-wide segment
-          const float4 h4 = make_float4(sh[4 * q], sh[4 * q + 1], sh[4 * q + 2], sh[4 * q + 3]);
-          const float4 l4 = make_float4(sl[4 * q], sl[4 * q + 1], sl[4 * q + 2], sl[4 * q + 3]);
-          const int per = Rp8 / 4;
-          *reinterpret_cast<float4*>(dsm + map.a1 + (size_t)(jr) * 2048 + p * 16) = h4;
-          *reinterpret_cast<float4*>(dsm + map.a1 + (size_t)(per + jr) * 2048 + p * 16) = l4;
-        }
-      }
-    }
-    fence_async();
-    tc_fence_before();
-    __syncthreads();
+    uint2 cnext = cfirst;
     // ---- MMA1: D1 = Sh*Ch^T + Sh*Cl^T + Sl*Ch^T ---------------------------------------------------
     if (issuer) {
       tc_fence_after();
@@ -666,6 +691,11 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
       }
     }
     d3_started = true;
+    const int ntile = tile + gridDim.x;
+    if (ntile < prm.n_tiles) {
+      stage_load_a1(ntile);
+      cfirst = first_codes(ntile);
+    }
     if (GRAD && !issuer) {
       // ---- gS tile out of D2 ---------------------------------------------------------------------
       dmbar_wait(&bar2, ph2);   // the last block's MMA2: D2 is complete
@@ -694,7 +724,9 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
     }
     nll_acc += (double)nll_part;
     nll_part = 0.0f;
-    // all TMEM reads of this tile are done before the next tile's MMAs overwrite D1 / D2
+    if (ntile < prm.n_tiles) stage_b3();   // (the epilogue warps have just waited for the last MMA3)
+    // the next tile's operands are staged and all TMEM reads of this tile are done before its MMAs overwrite D1 / D2
+    fence_async();
     tc_fence_before();
     __syncthreads();
   }
