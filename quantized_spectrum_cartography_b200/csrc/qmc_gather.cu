@@ -110,6 +110,7 @@ static int gather_impl(const float* S_dev, int64_t s_stride_b, int64_t s_stride_
                                                     : probit_scale(lik->noise_std);
   prm.inv_a = 1.0f / a;
   prm.offset = lik->offset;
+  prm.n_bounds = lik->n_bounds;
   for (int i = 0; i < lik->n_bounds; ++i) prm.bounds[i] = lik->bounds[i];
   prm.thr = lik->n_bounds >= 3 ? lik->bounds[1] : 0.0f;
 

@@ -47,6 +47,7 @@ struct GatherParams {
   float inv_a, offset;
   float thr;  // one-bit fast path threshold
   int one_sided;  // logistic model: three boundaries whose outer two are numerically infinite
+  int n_bounds;   // entries of bounds[] in use
   float bounds[QMC_MAX_BOUNDS];
 };
 
@@ -56,33 +57,46 @@ __device__ __forceinline__ int fast_div(uint32_t n, uint32_t magic, int shift) {
   return (int)(__umulhi(n, magic) >> shift);
 }
 
-template <int EPI, bool LOGD>
-__device__ __forceinline__ BinEval eval_entry(const GatherParams& prm, float t, int lvl, float& dxdt) {
+// bnd: the boundary table -- prm.bounds (kernel-parameter bank: a per-lane level makes it a divergent constant
+// access, replayed once per distinct level of the warp) or a copy in shared memory (lanes kernel: a plain gather).
+// FASTLOG: SFU-grade log link (lg2.approx is good to 2^-22 absolute in log2 units, far below what the bin widths can
+// see; a non-positive argument gives NaN / -inf exactly as logf does); never for the reference's literal epilogue.
+template <int EPI, bool LOGD, bool FASTLOG = false>
+__device__ __forceinline__ BinEval eval_entry(const GatherParams& prm, const float* __restrict__ bnd, float t, int lvl, float& dxdt) {
   float x = t;
   dxdt = 1.0f;
   if (LOGD) {
     const float u = t + prm.offset;
-    x = logf(u);
-    dxdt = 1.0f / u;
+    if (FASTLOG && EPI != EPI_REFERENCE) {
+      x = kLn2 * lg2_approx(u);
+      dxdt = rcp_approx(u);
+    } else {
+      x = logf(u);
+      dxdt = 1.0f / u;
+    }
   }
   if (EPI == EPI_LSQ) {
     // masked least squares on the bin mid-point (quantization_model_log.py:43-51, qmc_dowjons.ipynb c1:112):
     // "logp" = -(x - mid)^2 so that the callers' nll -= logp accumulates the squared residual
-    const float d = x - 0.5f * (prm.bounds[lvl] + prm.bounds[lvl + 1]);
+    const float d = x - 0.5f * (bnd[lvl] + bnd[lvl + 1]);
     BinEval o;
     o.logp = -d * d;
     o.gx = 2.0f * d;
     return o;
   } else if (EPI == EPI_LOGISTIC) {
     if (prm.one_sided) return logistic_one_sided_fast(prm.thr, lvl ? prm.inv_a : -prm.inv_a, x);  // uniform branch
-    return logistic_bin(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
+    return logistic_bin(bnd[lvl], bnd[lvl + 1], x, prm.inv_a);
   } else if (EPI == EPI_ONEBIT) {
     return probit_one_sided_fast(prm.thr, lvl ? -prm.inv_a : prm.inv_a, x);
   } else if (EPI == EPI_REFERENCE) {
-    return probit_bin_reference(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
+    return probit_bin_reference(bnd[lvl], bnd[lvl + 1], x, prm.inv_a);
   } else {
-    return probit_bin_stable<true>(prm.bounds[lvl], prm.bounds[lvl + 1], x, prm.inv_a);
+    return probit_bin_stable<true>(bnd[lvl], bnd[lvl + 1], x, prm.inv_a);
   }
+}
+template <int EPI, bool LOGD>
+__device__ __forceinline__ BinEval eval_entry(const GatherParams& prm, float t, int lvl, float& dxdt) {
+  return eval_entry<EPI, LOGD, false>(prm, prm.bounds, t, lvl, dxdt);
 }
 
 constexpr size_t kPrivateGcBytes = 32 * 1024;

@@ -118,6 +118,13 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   __shared__ uint64_t mbar[8];
   __shared__ double wsum[8];
   __shared__ int done;
+  // multi-level epilogues: the boundary table in shared memory (per-lane levels: a gather instead of a divergent
+  // constant-bank index); not needed, and not allocated, by the packed one-bit epilogue
+  constexpr bool NEED_BND = !(EPI == EPI_ONEBIT);
+  __shared__ float bnd_sm[NEED_BND ? QMC_MAX_BOUNDS + 1 : 1];
+  if (NEED_BND) {
+    for (int i = threadIdx.x; i < prm.n_bounds; i += blockDim.x) bnd_sm[i] = prm.bounds[i];   // before the CTA barrier below
+  }
 
   const int b = blockIdx.x / prm.tiles_per_map;
   const int tile = blockIdx.x - b * prm.tiles_per_map;
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
       for (int j = 0; j < 4; ++j) {
         const int lv = ok[j] ? w_level(w[j]) : 0;
         float dxdt;
-        const BinEval ev = eval_entry<EPI, LOGD>(prm, t[j], (EPI == EPI_ONEBIT) ? (lv & 1) : lv, dxdt);
+        const BinEval ev = eval_entry<EPI, LOGD, true>(prm, NEED_BND ? bnd_sm : prm.bounds, t[j], (EPI == EPI_ONEBIT) ? (lv & 1) : lv, dxdt);
         nll_part -= ok[j] ? ev.logp : 0.0f;
         g[j] = ok[j] ? ev.gx * dxdt : 0.0f;
       }
