@@ -300,6 +300,15 @@ def run_reference(args, rank: int, world: int):
     }))
 
 
+def measured_hbm_peak():
+    """(GB/s, where it comes from): the driver-measured copy bandwidth, else the profiling recipe's fallback."""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
 def _timed(fn, n, stream, barrier):
     """Mean device time of fn() in ms over n calls, max over ranks taken by the caller."""
     import torch
@@ -442,6 +451,11 @@ def cfg4_record(args, rank, world, dev, barrier, reduce_max):
     best = min(v["ms_per_eval"] for v in rec["modes"].values())
     rec["algorithmic_bytes"] = d.algorithmic_bytes(R)
     rec["mma_tflops"] = 3 * 2.0 * IJ * K * R / (best * 1e-3) / 1e12
+    rec["hbm_frac"] = rec["algorithmic_bytes"] / (best * 1e-3) / 1e9 / measured_hbm_peak()[0] if world == 1 else None
+    cpath = os.path.join(ROOT, "profiles", "dense_counters.json")     # ncu counters of the same kernel (not live)
+    if os.path.exists(cpath):
+        with open(cpath) as f:
+            rec["ncu"] = json.load(f)
     return rec
 
 
@@ -644,11 +658,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         return
 
     # ---- roofline -----------------------------------------------------------------------------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = measured_hbm_peak()
     alg_bytes = obs.algorithmic_bytes(R)
     mean_launch_ms = statistics.mean(per_launch_ms)
     achieved = alg_bytes / (mean_launch_ms * 1e-3) / 1e9
