@@ -179,13 +179,26 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   constexpr int NU = RP <= 4 ? 11 : RP == 8 ? 5 : 2;   // pixels per lane in flight (registers: NU * RP)
   const bool em_rows = !bulk && prm.sP == 1 && (RP % 4) == 0;
   float emv[(RP % 4) == 0 ? NU : 1][RP];
+  const int em_rem = sln - lane;   // pixel u * 32 + lane is inside the slice iff u * 32 < em_rem
   if (em_rows) {
-    const float* src = Sb + (int64_t)(p0 + sl0) + lane;
+    // one base pointer per emitter row; the loads then differ by immediate offsets only, and one comparison per
+    // pixel is the whole predicate when the rank is its own padded rank (the usual case)
+    const float* erow[RP];
 #pragma unroll
-    for (int u = 0; u < NU; ++u) {
+    for (int r = 0; r < RP; ++r) erow[r] = Sb + (int64_t)(r < prm.R ? r : 0) * prm.sR + (p0 + sl0) + lane;
+    if (prm.R == RP) {
 #pragma unroll
-      for (int r = 0; r < RP; ++r)
-        emv[u][r] = (u * 32 + lane < sln && r < prm.R) ? __ldg(src + (int64_t)r * prm.sR + u * 32) : 0.0f;
+      for (int u = 0; u < NU; ++u) {
+        const bool in = u * 32 < em_rem;
+#pragma unroll
+        for (int r = 0; r < RP; ++r) emv[u][r] = in ? __ldg(erow[r] + u * 32) : 0.0f;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+#pragma unroll
+        for (int r = 0; r < RP; ++r) emv[u][r] = (u * 32 < em_rem && r < prm.R) ? __ldg(erow[r] + u * 32) : 0.0f;
+      }
     }
   } else if (!bulk) {
     // any other strides: the slice is transposed into [p][r] rows by 4-byte asynchronous copies, all in flight at
@@ -252,13 +265,13 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
   }
   if (em_rows) {
     if constexpr ((RP % 4) == 0) {
+      float* srow = Sw + lane * RP;
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
-        const int pl = u * 32 + lane;
-        if (pl < sln) {
+        if (u * 32 < em_rem) {
 #pragma unroll
           for (int r = 0; r < RP; r += 4)
-            *reinterpret_cast<float4*>(Sw + pl * RP + r) = make_float4(emv[u][r], emv[u][r + 1], emv[u][r + 2], emv[u][r + 3]);
+            *reinterpret_cast<float4*>(srow + u * 32 * RP + r) = make_float4(emv[u][r], emv[u][r + 1], emv[u][r + 2], emv[u][r + 3]);
         }
       }
       // slices longer than 32 * NU pixels: the rest in further rounds (each one a memory round trip)
@@ -642,16 +655,33 @@ __global__ void __launch_bounds__(256, 2) gather_lanes_kernel(const GatherParams
     } else {
       __syncwarp();
       if (prm.sP == 1 && (RP % 4) == 0) {
-        // emitter-major rows: lane = pixel, one 16-byte read of the tile row per 4 emitters, R coalesced 4-byte stores
-        float* dst = gSb + (int64_t)(p0 + sl0);
-        for (int pl = lane; pl < sln; pl += 32) {
+        // emitter-major rows: lane = pixel, one 16-byte read of the tile row per 4 emitters, R coalesced 4-byte stores;
+        // one base pointer per emitter row, immediate offsets from there
+        float* drow[RP];
 #pragma unroll
-          for (int r = 0; r < RP; r += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(gSw + pl * RP + r);
-            if (r < prm.R) __stcg(dst + (int64_t)r * prm.sR + pl, v.x);
-            if (r + 1 < prm.R) __stcg(dst + (int64_t)(r + 1) * prm.sR + pl, v.y);
-            if (r + 2 < prm.R) __stcg(dst + (int64_t)(r + 2) * prm.sR + pl, v.z);
-            if (r + 3 < prm.R) __stcg(dst + (int64_t)(r + 3) * prm.sR + pl, v.w);
+        for (int r = 0; r < RP; ++r) drow[r] = gSb + (int64_t)(r < prm.R ? r : 0) * prm.sR + (p0 + sl0) + lane;
+        const float* grow = gSw + lane * RP;
+        const int rem = sln - lane;
+        for (int base = 0; base < sln; base += 32 * NU) {
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            if (base + u * 32 < rem) {
+#pragma unroll
+              for (int r = 0; r < RP; r += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(grow + (base + u * 32) * RP + r);
+                if (prm.R == RP) {
+                  __stcg(drow[r] + base + u * 32, v.x);
+                  __stcg(drow[r + 1] + base + u * 32, v.y);
+                  __stcg(drow[r + 2] + base + u * 32, v.z);
+                  __stcg(drow[r + 3] + base + u * 32, v.w);
+                } else {
+                  if (r < prm.R) __stcg(drow[r] + base + u * 32, v.x);
+                  if (r + 1 < prm.R) __stcg(drow[r + 1] + base + u * 32, v.y);
+                  if (r + 2 < prm.R) __stcg(drow[r + 2] + base + u * 32, v.z);
+                  if (r + 3 < prm.R) __stcg(drow[r + 3] + base + u * 32, v.w);
+                }
+              }
+            }
           }
         }
       } else {
