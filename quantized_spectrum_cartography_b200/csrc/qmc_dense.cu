@@ -4,10 +4,10 @@
 // neither X nor g = dNLL/dX ever exists in HBM.  Replaces the same reference idiom as the gather
 // kernels (qmc/quantization_model.py:22-39,57-61,70-86; qmc/qmc.ipynb c1:145-153).
 //
-// Per CTA (256 threads, persistent over 128-pixel tiles):
+// Per CTA (16 epilogue warps + 2 warps that only issue tensor-core instructions, persistent over tiles of up to 128 pixels):
 //   MMA1  D1[128 px x K bands]  = S_tile * C^T          kind::tf32, 3xTF32 split (hi*hi + hi*lo + lo*hi: three
 //         descriptor walks over the same [Sh|Sl] and [Ch|Cl] operand tiles)
-//   epilogue (8 warps): tcgen05.ld a 32-column slab of D1 per thread, read the 1-byte codes of the
+//   epilogue (16 warps): tcgen05.ld an 8-column slab of D1 per thread, read the 1-byte codes of the
 //         same entries, evaluate log P and g, store g (hi/lo TF32 parts) into shared memory twice:
 //         G[128 px x 32 bands] with bands contiguous and G^T[32 bands x 128 px] with pixels contiguous,
 //         both as K-major UMMA operands (MN-major TF32 operands in the no-swizzle layout read as zeros
@@ -30,7 +30,7 @@ constexpr int DT_PIX = 128;    // pixels per tile = TMEM lanes
 constexpr int DT_BLK = 32;     // bands per G block
 constexpr int DT_RP = 16;      // padded rank of the gradient MMAs (N)
 constexpr int DT_THREADS = 512;   // 16 epilogue warps: 4 per TMEM lane quadrant, each takes an 8-band slab of a block
-constexpr int DT_LAUNCH = DT_THREADS + 32;   // + one warp that only issues the tensor-core instructions
+constexpr int DT_LAUNCH = DT_THREADS + 64;   // + two warps that only issue tensor-core instructions (MMA1 + MMA2, MMA3)
 constexpr int DT_SLAB = DT_BLK / (DT_THREADS / 128);
 constexpr uint32_t TMEM_COLS = 512;
 #ifndef QMC_DENSE_NCH
@@ -381,11 +381,14 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
   //  branch is warp-uniform code that may use the uniform datapath)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant, which 8-band slab of a 32-band block
-  // Warp specialisation: warps 0..15 evaluate the likelihood and write the G operands; warp 16 issues every
-  // tcgen05.mma.  The epilogue warps hand a block's G over through the `gfull` mbarrier and go straight on to the next
-  // block's arithmetic -- they never wait for each other (no CTA barrier inside a tile) nor for the issue of ~60 MMA
-  // instructions; they only wait (bar2) for the previous block's MMAs before overwriting the G buffers.
-  const bool issuer = warp == DT_THREADS / 32;
+  // Warp specialisation: warps 0..15 evaluate the likelihood and write the G operands; warps 16 and 17 issue the
+  // tcgen05.mma instructions (16: MMA1 and MMA2, 17: MMA3).  The epilogue warps hand a block's G over through the `gfull`
+  // mbarrier and go straight on to the next block's arithmetic -- they never wait for each other (no CTA barrier
+  // inside a tile) nor for the issue of ~60 MMA instructions; they only wait for the previous block's MMA2 (bar2)
+  // before overwriting the G buffer and for MMA3 of the block before that (bar3) before overwriting its G^T buffer.
+  // Two issuing warps: the 48 instructions of a block's MMA3 (~15 issue-side instructions each) do not hold up the 12
+  // of the next MMA2, and a tcgen05.commit tracks the committing thread's own MMAs, so bar2 and bar3 separate cleanly.
+  const bool issuer = warp >= DT_THREADS / 32, issuer2 = warp == DT_THREADS / 32;
   const int row = quad * 32 + lane;              // pixel row of this thread inside the tile
   const uint32_t sbase = s_u32(dsm);
 
@@ -514,7 +517,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
     const uint8_t* crow = prm.code + (size_t)(p0 + pix) * K;
     uint2 cnext = cfirst;
     // ---- MMA1: D1 = Sh*Ch^T + Sh*Cl^T + Sl*Ch^T ---------------------------------------------------
-    if (issuer) {
+    if (issuer2) {
       tc_fence_after();
       const int per = Rp8 / 4;   // 16-byte chunks per segment
       for (int term = 0; term < 3; ++term) {
@@ -544,6 +547,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
           tc_fence_after();
           // MMA2: D2[128 x 16] += G_blk * C_blk   (K = 32 bands of this block, 4 steps of 8).  A descriptor's start
           // address field counts 16-byte units: stepping through an operand is an add on the descriptor.
+          if (issuer2) {
           if (!(prm.debug & 2)) {
 #pragma unroll
             for (int term = 0; term < 3; ++term) {
@@ -556,6 +560,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
             }
           }
           umma_commit(&bar2);   // the G buffer is free again
+          } else {
           // MMA3: D3_blk[bands x 16] += G_blk^T * S_tile   (K = 128 pixels, 16 steps of 8; M = 64
           // instruction whose rows 32..63 read the following chunk and are never looked at)
           const uint32_t gtb = map.gt + (uint32_t)(blk & 1) * 2 * GT_BYTES;
@@ -571,6 +576,7 @@ __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams p
             }
           }
           umma_commit(&bar3[blk & 1]);   // this block's G^T buffer is free again
+          }
         }
         phg ^= 1;
         continue;
