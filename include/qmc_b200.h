@@ -263,8 +263,9 @@ QMC_API int64_t qmc_dense_smem_bytes(int K, int R);
  * An exchange region is device memory of qmc_peer_region_bytes() bytes allocated by qmc_peer_alloc (which also
  * returns the 64-byte CUDA IPC handle the other ranks open with qmc_peer_open; exchange the handles with any host
  * mechanism, e.g. torch.distributed.all_gather_object).  All ranks must issue the same sequence of exchange calls
- * on a region set; a peer that never arrives makes the kernel give up after ~2 s and set the region's status word
- * (qmc_peer_status != 0). */
+ * on a region set, with the same world, slot_floats, K and R; a peer that never arrives makes the kernel give up after
+ * ~2 s, hand back this rank's own partial sums and set the region's status word (qmc_peer_status != 0).  Regions must
+ * outlive every launch that names them: synchronise all ranks before qmc_peer_close / qmc_peer_free. */
 #define QMC_PEER_MAX_WORLD 8
 typedef struct qmc_peer_exchange {
   int32_t rank, world;                 /* 1 <= world <= QMC_PEER_MAX_WORLD */

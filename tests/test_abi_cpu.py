@@ -107,3 +107,24 @@ def test_lanes_tile_of_cfg3_leaves_room_for_two_ctas_per_sm():
     assert b == (2 * 326 * 8 * 4 + 65 * 4 + 8 * (65 + 32) * 4 + 8 * 5 * 32 + 8 * 2 * 128) * 4 + 16
     assert 2 * (b + 1024 + 512) <= 228 * 1024
     assert _lib.lib.qmc_lanes_smem_bytes(64, 4, 100000, 8, 5, 16) == 0
+
+
+def test_exchange_region_geometry_and_descriptor_mirror():
+    """The fused exchange's host-side helpers need no GPU: region size = 256-byte header + scratch slot + two sets of
+    `world` slots; the ctypes mirror of qmc_peer_exchange_t has the header's layout; bad geometries give 0."""
+    import ctypes as C
+
+    from quantized_spectrum_cartography_b200 import _lib
+    rb = _lib.lib.qmc_peer_region_bytes
+    assert rb(8, 4100) == 256 + (1 + 2 * 8) * 4100 * 4
+    assert rb(1, 4) == 256 + 3 * 16
+    assert rb(0, 4100) == 0 and rb(9, 4100) == 0 and rb(2, 4098) == 0 and rb(2, 0) == 0
+    px = _lib.PeerExchange
+    assert _lib.QMC_PEER_MAX_WORLD == 8
+    assert (px.rank.offset, px.world.offset, px.slot_floats.offset, px.region.offset) == (0, 4, 8, 16)
+    assert C.sizeof(px) == 16 + 8 * C.sizeof(C.c_void_p)
+    hdr = open(os.path.join(ROOT, "include", "qmc_b200.h")).read()
+    assert "#define QMC_PEER_MAX_WORLD 8" in hdr
+    # the dense smem budget the kernel asks for at cfg4 (K = 256, R = 16) fits the 227 KB a CTA may have
+    assert 0 < _lib.lib.qmc_dense_smem_bytes(256, 16) <= 227 * 1024 - 4096
+    assert _lib.lib.qmc_dense_smem_bytes(288, 16) == 0 and _lib.lib.qmc_dense_smem_bytes(256, 17) == 0
