@@ -365,7 +365,7 @@ __host__ __device__ inline DenseSmem dense_smem_map(int K, int Rp8) {
 }
 
 // NCH: independent likelihood evaluations per lane and pass of the compacted queue (instruction-level parallelism for
-// the ~17 warps of the CTA: 4 passes a slab's ~128 observed entries in one go)
+// the 18 warps of the CTA: 4 passes a slab's ~128 observed entries in one go)
 template <int EPI, bool LOGD, bool GRAD, int NCH>
 __global__ void __launch_bounds__(DT_LAUNCH, 1) dense_kernel(const DenseParams prm) {
   extern __shared__ __align__(1024) uint8_t dsm[];
