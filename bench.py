@@ -398,6 +398,12 @@ def cfg4_record(args, rank, world, dev, barrier, reduce_max):
         try:
             inst.evaluate(Sl, Cm, gather_gS=False, cuda_graph=True)
         except Exception as e:                               # NCCL capture unavailable: time the eager sequence
+            if exchange == "peer":
+                # no CUDA IPC between the ranks' processes on this box (every rank gets the same verdict and raises
+                # together, dense.PeerRegions): the NCCL forms above stand
+                rec["modes"][tag] = {"unavailable": str(e)[:300]}
+                del inst
+                continue
             use_graph = False
             inst._graph = None
             torch.cuda.synchronize()
@@ -448,7 +454,7 @@ def cfg4_record(args, rank, world, dev, barrier, reduce_max):
         rec["modes"][tag] = m
         del inst
     d = dense.DenseObs(torch.empty(0), IJ, K, nobs, 0)
-    best = min(v["ms_per_eval"] for v in rec["modes"].values())
+    best = min(v["ms_per_eval"] for v in rec["modes"].values() if "ms_per_eval" in v)
     rec["algorithmic_bytes"] = d.algorithmic_bytes(R)
     rec["mma_tflops"] = 3 * 2.0 * IJ * K * R / (best * 1e-3) / 1e12
     rec["hbm_frac"] = rec["algorithmic_bytes"] / (best * 1e-3) / 1e9 / measured_hbm_peak()[0] if world == 1 else None

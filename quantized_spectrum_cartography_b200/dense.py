@@ -59,8 +59,9 @@ def pack_dense(Y: torch.Tensor, Wx: Optional[torch.Tensor], K: int) -> DenseObs:
 class PeerRegions:
     """Exchange regions of the fused factor-gradient exchange (``qmc_nll_fwd_bwd_dense_exchange``): this rank's own
     region (``qmc_peer_alloc``) and the peers' regions opened through CUDA IPC.  ``share`` is the host mechanism that
-    hands the 64-byte handles around: a callable ``handle_bytes -> list of every rank's handle bytes`` (default:
-    ``torch.distributed.all_gather_object``)."""
+    hands the 64-byte handles (and, in a second round, every rank's verdict) around: a callable ``obj -> list of every
+    rank's obj`` (default: ``torch.distributed.all_gather_object``).  If any rank cannot allocate or map a region, ALL
+    ranks raise ``QmcError`` -- nobody is left waiting."""
 
     def __init__(self, rank: int, world: int, slot_floats: int, device, share=None):
         if not 1 <= world <= _lib.QMC_PEER_MAX_WORLD:
@@ -71,9 +72,16 @@ class PeerRegions:
         own = C.c_void_p()
         handle = (C.c_ubyte * 64)()
         self._opened: list[int] = []
+        self._own = None
         with torch.cuda.device(self.device):
-            check(lib.qmc_peer_alloc(nbytes, C.byref(own), handle))
-            self._own = own.value
+            # A rank that fails must not leave its peers waiting in the hand-shake: every rank always takes part in both
+            # rounds (handles, then "did every mapping work"), and all ranks raise together.
+            err = None
+            try:
+                check(lib.qmc_peer_alloc(nbytes, C.byref(own), handle))
+                self._own = own.value
+            except Exception as e:          # noqa: BLE001 -- reported to every rank below
+                err = repr(e)
             if share is None:
                 import torch.distributed as dist
 
@@ -81,17 +89,29 @@ class PeerRegions:
                     got = [None] * world
                     dist.all_gather_object(got, h)
                     return got
-            handles = share(bytes(handle)) if world > 1 else [bytes(handle)]
+            mine = None if err else bytes(handle)
+            handles = share(mine) if world > 1 else [mine]
             self.px = _lib.PeerExchange()
             self.px.rank, self.px.world, self.px.slot_floats = rank, world, self.slot_floats
-            for q in range(world):
-                if q == rank:
-                    self.px.region[q] = self._own
-                    continue
-                ptr = C.c_void_p()
-                check(lib.qmc_peer_open((C.c_ubyte * 64).from_buffer_copy(handles[q]), C.byref(ptr)))
-                self._opened.append(ptr.value)
-                self.px.region[q] = ptr.value
+            if err is None and all(h is not None for h in handles):
+                try:
+                    for q in range(world):
+                        if q == rank:
+                            self.px.region[q] = self._own
+                            continue
+                        ptr = C.c_void_p()
+                        check(lib.qmc_peer_open((C.c_ubyte * 64).from_buffer_copy(handles[q]), C.byref(ptr)))
+                        self._opened.append(ptr.value)
+                        self.px.region[q] = ptr.value
+                except Exception as e:      # noqa: BLE001
+                    err = repr(e)
+            elif err is None:
+                err = "a peer could not allocate its exchange region"
+            verdicts = share(err) if world > 1 else [err]
+            bad = [f"rank {q}: {v}" for q, v in enumerate(verdicts) if v is not None]
+            if bad:
+                self.close()
+                raise _lib.QmcError("fused exchange unavailable (" + "; ".join(bad) + ")")
 
     def status(self) -> int:
         """0 = every exchange so far completed; 1 = a peer never arrived (the kernel gave up after ~2 s).  Synchronises
